@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the B200-native RV log-likelihood path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): RV lnL evals/sec (K-planet, batched), plus the fraction of the FP64
+roofline.  Workload at every N: BASELINE.json configs[1] -- 2-planet eccentric + linear drift,
+2 instruments, 1000 epochs, one vectorised batch of ndraw = 4096 parameter vectors per step and
+per GPU (weak scaling: rows sharded over ranks, lnL all-gathered over NCCL inside the step).
+
+One JSON line on stdout (rank 0).  `value` = device-timed throughput with theta resident in HBM;
+`e2e` = the same metric through the public host-buffer API (pinned host theta -> H2D -> kernel ->
+D2H lnL) ; `roofline` = algorithmic FP64 flops of the likelihood kernel / its CUDA-event time /
+the FP64 peak measured in the same run by a register-resident DFMA loop (MEASURED_PEAKS.json has
+no FP64 row); `cpu_baseline` = the CPU oracle (numpy restatement + the reference's own C Kepler
+solver from oracle/_ref) on the box's host cores.
+
+`--impl reference` times that CPU implementation alone, on the same config/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RV lnL evals/sec (K-planet, batched)"
+UNIT = "lnL/s"
+CONFIG_ID = 2
+BATCH = 4096
+
+
+def algorithmic_flops(n_epochs, n_planets, drift_order, mean_iters):
+    """F = N [K (51 + 46 I) + 48 + 2 d] FP64 flops per lnL."""
+    return n_epochs * (n_planets * (51.0 + 46.0 * mean_iters) + 48.0 + 2.0 * drift_order)
+
+
+def workload_config(case, batch, world):
+    return {"workload": f"config{CONFIG_ID}: {case.n_planets}-planet Keplerian + "
+                        f"{'linear drift' if case.drift else 'no drift'}, {case.n_inst} instruments, "
+                        f"{case.n_epochs} epochs, batch {batch} theta per step per GPU "
+                        f"(UltraNest vectorized ndraw={batch})",
+            "n_epochs": case.n_epochs, "n_planets": case.n_planets, "n_inst": case.n_inst,
+            "ndim": case.ndim, "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": f"rows sharded x{world}, lnL all-gather",
+            "l2": "flushed (256 MiB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle (test infrastructure) timed on the host cores
+# ------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(fixed, tables, parnames):
+    from oracle.rv_oracle import OracleRVModel
+    _W["m"] = OracleRVModel(fixed, tables, parnames)
+
+
+def _cpu_eval(block):
+    return _W["m"].log_likelihood_batch(block)
+
+
+def cpu_rate(case, theta, cores, budget_s=12.0):
+    """lnL/s of the CPU oracle on `cores` processes over a bounded sample of `theta`."""
+    import multiprocessing as mp
+    from oracle import rv_oracle
+    rv_oracle.build()
+    kind = rv_oracle.solver_kind()
+    tables = case.datadict()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init,
+                  initargs=(case.fixedpardict, tables, case.parnames)) as pool:
+        probe = theta[: max(cores * 8, 64)]
+        t0 = time.perf_counter()
+        pool.map(_cpu_eval, np.array_split(probe, cores))
+        rate0 = len(probe) / (time.perf_counter() - t0)
+        n = int(min(len(theta), max(len(probe), rate0 * budget_s)))
+        sample = theta[:n]
+        t0 = time.perf_counter()
+        pool.map(_cpu_eval, np.array_split(sample, cores * 4))
+        dt = time.perf_counter() - t0
+    return n / dt, n, dt, kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from evidence_b200 import synth
+    case = synth.make_case(CONFIG_ID)
+    cores = os.cpu_count() or 1
+    theta = case.draw_theta(max(BATCH, 4096), seed=1000)
+    rates = []
+    n = dt = 0
+    kind = "port"
+    for k in range(args.warmup + args.steps):
+        r, n, dt, kind = cpu_rate(case, theta, cores, budget_s=max(2.0, 60.0 / max(1, args.steps)))
+        if k >= args.warmup:
+            rates.append(r)
+    value = float(np.mean(rates)) if rates else 0.0
+    sample = (f"{n} of {len(theta)} theta rows per step on {cores} processes "
+              f"(numpy restatement of RVModel.log_likelihood; Kepler solver = "
+              f"{'the reference trueanomaly.c compiled to oracle/_ref' if kind == 'reference' else 'C restatement'})")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * n / value if value else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(case, BATCH, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "power_w_max": float(np.max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def sweep(model_factory, case, batch, steps, torch, peak_tflops):
+    """A larger parameter sweep of another BASELINE shape (extra information, N=1 only)."""
+    model = model_factory(case)
+    theta = torch.from_numpy(case.draw_theta(batch, seed=77)).cuda()
+    out = torch.empty(batch, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        model.log_likelihood_device(theta, out=out)
+    torch.cuda.synchronize()
+    model.reset_counters()
+    kms = []
+    for _ in range(steps):
+        model.log_likelihood_device(theta, out=out)
+        kms.append(model.last_kernel_ms())
+    c = model.counters()
+    mean_it = c["n_newton_iters"] / max(1, c["n_solves"])
+    F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
+    ms = float(np.mean(kms))
+    rate = batch / (ms * 1e-3)
+    ach = rate * F / 1e12
+    res = {"workload": f"N={case.n_epochs} K={case.n_planets} inst={case.n_inst} batch={batch}",
+           "lnl_per_s": rate, "kepler_solves_per_s": rate * case.n_epochs * case.n_planets,
+           "kernel_ms": ms, "mean_newton_iters": mean_it, "achieved_tflops": ach,
+           "frac_of_fp64_peak": ach / peak_tflops if peak_tflops else None}
+    model.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline and sweeps")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from evidence_b200 import build, synth
+    from evidence_b200.multigpu import ShardedLikelihood
+    from evidence_b200.rvmodel import RVModel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def make_model(case):
+        return RVModel(case.fixedpardict, case.datadict(), case.parnames, device=local_rank)
+
+    case = synth.make_case(CONFIG_ID)
+    model = make_model(case)
+    B, K, W = args.batch, args.steps, args.warmup
+    theta_host = case.draw_theta(B, seed=1000 + rank)
+    theta = torch.from_numpy(theta_host).cuda()
+    lnl = torch.empty(B, dtype=torch.float64, device="cuda")
+    sharded = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk, out=lnl), case.ndim)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        return sharded.evaluate_local(theta)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak = model.fp64_peak_tflops()
+    for _ in range(W):
+        step()
+    barrier()
+    model.reset_counters()
+    launches0 = model.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    kms = []
+    clocks = ClockSampler(local_rank)
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(K):
+        flush.zero_()  # L2 flush, outside the per-step events
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+        kms.append(model.last_kernel_ms())
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clk = clocks.stop()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    launches = model.launch_count() - launches0
+    cnt = model.counters()
+
+    # ---- end to end: pinned host theta -> H2D -> kernel(s) -> D2H lnL, public host API ----
+    th_pin = torch.from_numpy(theta_host).pin_memory()
+    out_pin = torch.empty(B, dtype=torch.float64).pin_memory()
+    th_np, out_np = th_pin.numpy(), out_pin.numpy()
+    out_all_pin = torch.empty(B * world, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        if world == 1:
+            model.log_likelihood_batch(th_np, out=out_np)  # rvl_loglike: H2D, kernel, D2H, sync
+        else:  # H2D, kernel, NCCL all-gather, D2H of the gathered vector (what a sampler sees)
+            theta.copy_(th_pin, non_blocking=True)
+            gathered = sharded.evaluate_local(theta)
+            out_all_pin.copy_(gathered, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        red = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(red[0]), float(red[1])
+
+    mean_it = cnt["n_newton_iters"] / max(1, cnt["n_solves"])
+    F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
+    k_ms = float(np.mean(kms))
+    achieved = B * F / (k_ms * 1e-3) / 1e12
+    value = world * B * K / (dev_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(case, B, world),
+        "clocks": clk,
+        "e2e": {"value": world * B * K / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(B * case.ndim * 8), "d2h_bytes_per_step": int(B * 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "kernel": "rv_lnl_kernel", "kernel_ms": k_ms,
+                     "flops_per_lnl": F, "mean_newton_iters": mean_it,
+                     "peak_source": "DFMA loop measured in this run (rvl_fp64_peak); "
+                                    "MEASURED_PEAKS.json has no FP64 row",
+                     "hbm_bytes_per_lnl": 8 * (case.ndim + 1)},
+        "wall_s_timed_region": t_wall,
+        "kepler_solves_per_s": value * case.n_epochs * case.n_planets,
+        "newton_cap_hits": cnt["n_cap_hits"],
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            sweeps = []
+            sweeps.append(sweep(make_model, synth.make_case(3), 65536, 5, torch, peak))
+            sweeps.append(sweep(make_model, synth.make_case(5), 32768, 3, torch, peak))
+            line["sweeps"] = sweeps
+        except Exception as exc:  # extras must never cost the headline line
+            line["sweeps_error"] = repr(exc)
+        try:
+            cores = os.cpu_count() or 1
+            rate, n, dt, kind = cpu_rate(case, theta_host, cores, budget_s=12.0)
+            rate1, n1, dt1, _ = cpu_rate(case, theta_host, 1, budget_s=5.0)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n} of the {B} theta rows of one step, {dt:.1f} s on {cores} processes; "
+                          f"numpy restatement of RVModel.log_likelihood with "
+                          f"{'the reference trueanomaly.c (oracle/_ref)' if kind == 'reference' else 'the C restatement of trueanomaly'}"
+                          f"; single core: {rate1:.0f} lnL/s",
+                "single_core_value": rate1}
+        except Exception as exc:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": "failed: " + repr(exc)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,243 @@
+// rvl_math.h — the FP64 arithmetic core of the batched Kepler / RV log-likelihood kernel.
+//
+// Every function here is plain IEEE-754 double arithmetic written with explicit, never
+// contracted operations (mul/add/sub/fma helpers), so that the exact same source compiles for
+// sm_100a (the product: rvlnl.cu) and for the host (tests/host_emul, which replays the kernel's
+// arithmetic lane by lane on the CPU to validate numerics without a GPU).  The host build is a
+// test harness only; the product has no CPU path.
+//
+// Reference semantics reproduced (paths relative to the reference checkout):
+//   evidence/rvmodel/trueanomaly.c:8-41        Newton from E=M, |dE|<=tol stop, e clamp 0.99
+//   evidence/rvmodel/__init__.py:459           M = 2*pi/P * (t - epoch) + M0   (no FMA!)
+//   evidence/rvmodel/__init__.py:463           rv = K (cos(nu + w) + e cos w)
+//
+// Why the operation order matters: M and E live near 1e4 rad where one
+// ulp is 1.8e-12, and lnL responds to phase errors with a gain of ~1e4.  So the roundings that
+// happen ON that 1.8e-12 grid -- forming M, forming E - e sin E, and the Newton update
+// E - f/f' -- are reproduced operation for operation.  Everything that is small compared with
+// the grid (the quotient f/f', sin/cos values, the rotation to the true anomaly) only has to
+// be accurate to an ulp or two, which leaves room to make it cheap:
+//   * f/f' is f * rcp(f') with a 2-step Newton reciprocal (no IEEE division),
+//   * after a Newton step of size d, (sin E, cos E) is advanced by an angle-addition with a
+//     short series in d when every lane of the warp has |d| small (warp-uniform choice),
+//   * cos(nu), sin(nu) come from the closed form in (sin E, cos E) instead of atan(tan()).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define RVL_HD __host__ __device__ __forceinline__
+#else
+#define RVL_HD inline
+#endif
+
+namespace rvl {
+
+// ---- never-contracted primitives --------------------------------------------------------
+RVL_HD double mul(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;  // host harness is built with -ffp-contract=off
+#endif
+}
+RVL_HD double add(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+RVL_HD double sub(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+RVL_HD double fma_(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return ::fma(a, b, c);
+#endif
+}
+RVL_HD int32_t lo32(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int32_t)(uint32_t)u;
+#endif
+}
+RVL_HD int32_t hi32(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int32_t)(uint32_t)(u >> 32);
+#endif
+}
+RVL_HD double from_hilo(int32_t hi, int32_t lo)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+// ---- reciprocal: hardware seed + two Newton steps (4 DFMA), <= ~1 ulp --------------------
+// Valid for normal, finite x (denominators 1 - e cos E in [0.01, 2], variances).
+RVL_HD double rcp(double x)
+{
+    double y;
+#if defined(__CUDA_ARCH__)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RCP64H, ~20 bits
+#else
+    y = (double)(1.0f / (float)x);  // host harness stand-in for the hardware seed
+#endif
+    double e = fma_(-x, y, 1.0);
+    y = fma_(y, e, y);
+    e = fma_(-x, y, 1.0);
+    y = fma_(y, e, y);
+    return y;
+}
+
+// ---- sin & cos of an un-reduced angle ----------------------------------------------------
+// Cody-Waite reduction by pi/2 in three FMA steps (exact for |x| < ~1e5, like CUDA's own fast
+// path), then the classic degree-13/14 minimax kernels on [-pi/4, pi/4] (fdlibm coefficients).
+// 20 FP64 instructions; ~1 ulp.  Callers route |x| >= kTrigFastMax elsewhere.
+constexpr double kTrigFastMax = 100000.0;
+constexpr double kTwoOverPi = 0x1.45f306dc9c883p-1;
+constexpr double kPio2Hi = 0x1.921fb54442d18p+0;
+constexpr double kPio2Mid = 0x1.1a62633145c07p-54;
+constexpr double kPio2Lo = -0x1.f1976b7ed8fbcp-110;
+constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
+
+RVL_HD void sincos_fast(double x, double &s, double &c)
+{
+    const double q = fma_(x, kTwoOverPi, kMagic);
+    const int32_t n = lo32(q);
+    const double qf = sub(q, kMagic);
+    double r = fma_(-qf, kPio2Hi, x);
+    r = fma_(-qf, kPio2Mid, r);
+    r = fma_(-qf, kPio2Lo, r);
+    const double z = mul(r, r);
+    double ps = 1.58969099521155010221e-10;
+    ps = fma_(ps, z, -2.50507602534068634195e-08);
+    ps = fma_(ps, z, 2.75573137070700676789e-06);
+    ps = fma_(ps, z, -1.98412698298579493134e-04);
+    ps = fma_(ps, z, 8.33333333332248946124e-03);
+    ps = fma_(ps, z, -1.66666666666666324348e-01);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma_(pc, z, 2.08757232129817482790e-09);
+    pc = fma_(pc, z, -2.75573143513906633035e-07);
+    pc = fma_(pc, z, 2.48015872894767294178e-05);
+    pc = fma_(pc, z, -1.38888888888741095749e-03);
+    pc = fma_(pc, z, 4.16666666666666019037e-02);
+    const double sr = fma_(mul(r, z), ps, r);
+    const double cr = fma_(z, fma_(z, pc, -0.5), 1.0);
+    // quadrant: n mod 4 = 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s)   [integer pipe only]
+    const bool swp = (n & 1) != 0;
+    double ss = swp ? cr : sr;
+    double cc = swp ? sr : cr;
+    const uint32_t sflip = ((uint32_t)n & 2u) << 30;         // bit 31 set when n&2
+    const uint32_t cflip = (((uint32_t)n + 1u) & 2u) << 30;  // bit 31 set when (n+1)&2
+    s = from_hilo((int32_t)((uint32_t)hi32(ss) ^ sflip), lo32(ss));
+    c = from_hilo((int32_t)((uint32_t)hi32(cc) ^ cflip), lo32(cc));
+}
+
+// ---- advance (sin E, cos E) by a small step d: E <- E + d --------------------------------
+// s' = s + (c sin d - s (1 - cos d)),  c' = c - (s sin d + c (1 - cos d)).
+// Writing the update as "old value + small correction" keeps the added rounding error at half
+// an ulp per step however many steps are chained.
+// |d| <= 2^-10 : sin d = d - d^3/6 (next term 7e-18), 1-cos d = d^2/2 - d^4/24.   11 instr.
+RVL_HD void advance_tiny(double d, double &s, double &c)
+{
+    const double d2 = mul(d, d);
+    const double sd = fma_(mul(d, d2), -1.0 / 6.0, d);
+    const double v = mul(d2, fma_(d2, -1.0 / 24.0, 0.5));
+    const double ds = fma_(c, sd, -mul(s, v));
+    const double dc = fma_(s, sd, mul(c, v));
+    s = add(s, ds);
+    c = sub(c, dc);
+}
+// |d| <= 2^-5 : sin d through d^7 (next 8e-20), 1-cos d through d^8 (next 2e-22).   16 instr.
+RVL_HD void advance_small(double d, double &s, double &c)
+{
+    const double d2 = mul(d, d);
+    double ps = -1.0 / 5040.0;
+    ps = fma_(ps, d2, 1.0 / 120.0);
+    ps = fma_(ps, d2, -1.0 / 6.0);
+    const double sd = fma_(mul(d, d2), ps, d);
+    double pc = 1.0 / 40320.0;
+    pc = fma_(pc, d2, -1.0 / 720.0);
+    pc = fma_(pc, d2, 1.0 / 24.0);
+    pc = fma_(pc, d2, -0.5);
+    const double v = -mul(d2, pc);
+    const double ds = fma_(c, sd, -mul(s, v));
+    const double dc = fma_(s, sd, mul(c, v));
+    s = add(s, ds);
+    c = sub(c, dc);
+}
+constexpr double kTinyStep = 0x1p-10;
+constexpr double kSmallStep = 0x1p-5;
+
+// ---- one Newton step of Kepler's equation (trueanomaly.c:25-29) ---------------------------
+// Given E with (s, c) = (sin E, cos E):  f = (E - ec s) - M  [two grid roundings, as the
+// reference], f' = 1 - ec c, E_new = E - f * rcp(f') [one grid rounding].  Returns E_new - E,
+// which is exact (Sterbenz) and is the quantity the reference thresholds against tol (:21).
+RVL_HD double newton_step(double E, double s, double c, double M, double ec, double &Enew)
+{
+    const double r = rcp(fma_(-ec, c, 1.0));
+    const double f = sub(sub(E, mul(ec, s)), M);
+    Enew = fma_(-f, r, E);
+    return sub(Enew, E);
+}
+
+// ---- radial velocity of one planet at eccentric anomaly E ---------------------------------
+// K (cos(nu + w) + e cos w) with cos nu = (c - ec)/(1 - ec c), sin nu = sqrt(1-ec^2) s/(1 - ec c)
+//   = (A (c - ec) + Bs s) / (1 - ec c) + Ce,
+// A = K cos w, Bs = -K sin w sqrt(1 - ec^2), Ce = K (e cos w) with the UN-clamped e
+// (rvmodel/__init__.py:463).  10 instructions.
+RVL_HD double kepler_rv(double s, double c, double ec, double A, double Bs, double Ce)
+{
+    const double r = rcp(fma_(-ec, c, 1.0));
+    const double num = fma_(Bs, s, mul(A, sub(c, ec)));
+    return fma_(num, r, Ce);
+}
+
+// mean anomaly, exactly as the reference forms it (rvmodel/__init__.py:459): three roundings
+RVL_HD double mean_anomaly(double nmot, double t, double epoch, double M0)
+{
+    return add(mul(nmot, sub(t, epoch)), M0);
+}
+
+// ---- log-determinant bookkeeping: split var into mantissa in [1,2) and exponent ----------
+// sum_j ln(var_j) = ln(prod mant_j) + ln2 * sum exp_j.  Returns false for var that is zero,
+// subnormal, negative, inf or nan (caller falls back to plain log()).
+RVL_HD bool split_pos(double v, double &mant, int32_t &expo)
+{
+    const int32_t hi = hi32(v);
+    const uint32_t be = (uint32_t)hi >> 20;  // sign+biased exponent
+    expo = (int32_t)be - 1023;
+    mant = from_hilo((hi & 0x000fffff) | 0x3ff00000, lo32(v));
+    return (uint32_t)(be - 1u) < 0x7feu;
+}
+constexpr double kLn2Hi = 0x1.62e42fefa39efp-1;
+constexpr double kLn2Lo = 0x1.abc9e3b39803fp-56;
+
+}  // namespace rvl

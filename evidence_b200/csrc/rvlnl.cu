@@ -1,0 +1,1171 @@
+// rvlnl.cu — librvlnl.so: B200 (sm_100a) batched Keplerian RV log-likelihood + prior transform
+// behind the C-ABI of include/rvlnl.h.  No CPU fallback, no dispatch: sm_100a only.
+//
+// Reference path replaced (paths relative to the reference checkout):
+//   evidence/rvmodel/__init__.py:157-219  RVModel.log_likelihood      -> rv_lnl_kernel
+//   evidence/rvmodel/__init__.py:343-463  kep_rv / modelk             -> point_setup + solve_planet
+//   evidence/rvmodel/trueanomaly.c:8-41   trueanomaly()               -> solve_planet / trueanomaly_kernel
+//   evidence/rvmodel/__init__.py:222-273  drift                       -> epoch_term
+//   evidence/rvmodel/__init__.py:59-80    BaseModel.logL              -> epoch_term + slice reduce
+//   evidence/ultranest/__init__.py:125-137 prior(hypercube)           -> prior_transform_kernel
+//
+// Layout.  Epoch data lives in HBM as columns [ncol][Npad] of doubles (t, vrad, svrad^2, then
+// (t-tref)/365.25 when the model has a drift, then the linear-parameter columns) followed by
+// Npad instrument ids (uint8).  The epoch axis is cut into S slices of whole 32-epoch chunks;
+// block b serves slice b % S and brings that slice of every column into shared memory ONCE with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier), then stays resident: its warps pull parameter
+// vectors from a per-slice work counter.  warp <-> one parameter vector, lanes <-> 32 epochs:
+// all lanes of a warp share the eccentricity, so Newton iteration counts are nearly uniform and
+// the loop exit / sin-cos path choice are warp votes.  chi^2 and log-det partial sums are
+// reduced with warp shuffles; with S > 1 the per-slice partials are combined by a tiny second
+// kernel in a fixed order (deterministic).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/rvlnl.h"
+#include "rvl_math.h"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPlanetStride = 8;  // doubles per planet in the per-warp constant block
+constexpr int kModelBytes = (int)((sizeof(rvl_model_desc) + 127) / 128 * 128);
+// per-planet constants: 0 nmot, 1 M0, 2 ec, 3 A, 4 Bs, 5 Ce, 6 epoch
+
+struct KArgs {
+    const rvl_model_desc *model;  // device copy
+    const double *cols;           // [ncol][Npad]
+    const uint8_t *inst;          // [Npad]
+    const double *theta;          // [B][ndim]
+    double *lnl;                  // [B]        (written directly when S == 1)
+    double *partial;              // [B][S][2]  (S > 1)
+    int *flags;                   // [B] 1 = invalid Keplerian (S > 1)
+    unsigned long long *counters; // 0 newton iters, 1 cap hits, 2 invalid points
+    unsigned int *work;           // [S] dynamic work counters
+    long long B;
+    double cte;  // -0.5 N ln(2 pi)
+    int N, Npad, ncol;
+    int S, cps;  // slices, chunks per slice
+    int wstride; // doubles per warp in the constant block
+};
+
+// ---- shared-memory / TMA helpers (sm_90+ PTX) --------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D TMA: global -> shared, completion counted in bytes on the mbarrier.  bytes % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ double par_of(const rvl_param &p, const double *row)
+{
+    return p.slot >= 0 ? __ldg(row + p.slot) : p.value;
+}
+
+__device__ __noinline__ void sincos_slow(double x, double &s, double &c)
+{
+    sincos(x, &s, &c);  // CUDA libdevice: Payne-Hanek for huge arguments, NaN for inf/nan
+}
+__device__ __forceinline__ void sincos_any(double x, double &s, double &c)
+{
+    if (fabs(x) < rvl::kTrigFastMax)
+        rvl::sincos_fast(x, s, c);
+    else
+        sincos_slow(x, s, c);
+}
+
+// ---- one planet, one epoch per lane: Kepler solve + RV term -------------------------------
+// VARIANT 0: optimised (reciprocal-multiply Newton step, warp-uniform small-step sin/cos
+//            advance).  VARIANT 1: conservative (IEEE division, full sin/cos every step) — kept
+//            as the in-product cross-check of the optimisations, selectable with
+//            rvl_set_option("variant", 1).
+template <int VARIANT>
+__device__ __forceinline__ double solve_planet(double t, const double *pc, double tol, int itmax,
+                                               int &iters, int &caps)
+{
+    const double nmot = pc[0], M0 = pc[1], ec = pc[2], A = pc[3], Bs = pc[4], Ce = pc[5],
+                 epoch = pc[6];
+    const double M = rvl::mean_anomaly(nmot, t, epoch, M0);
+    double E = M, s, c;
+    sincos_any(E, s, c);
+    bool active = true;
+    int it = 0;
+    while (true) {
+        double d = 0.0;
+        if (active) {
+            double En;
+            if (VARIANT == 0) {
+                d = rvl::newton_step(E, s, c, M, ec, En);
+            } else {
+                const double f = rvl::sub(rvl::sub(E, rvl::mul(ec, s)), M);
+                const double fp = rvl::sub(1.0, rvl::mul(ec, c));
+                En = rvl::sub(E, __ddiv_rn(f, fp));
+                d = rvl::sub(En, E);
+            }
+            E = En;
+            ++it;
+            if (it >= itmax) {  // trueanomaly.c:32-33: the cap is tested before convergence
+                active = false;
+                ++caps;
+            } else if (!(fabs(d) > tol)) {  // trueanomaly.c:21
+                active = false;
+            }
+        }
+        const double ad = fabs(d);
+        if (VARIANT == 0 && __all_sync(kFull, ad <= rvl::kTinyStep)) {
+            rvl::advance_tiny(d, s, c);
+        } else if (VARIANT == 0 && __all_sync(kFull, ad <= rvl::kSmallStep)) {
+            rvl::advance_small(d, s, c);
+        } else {
+            double s2, c2;
+            sincos_any(E, s2, c2);
+            if (d != 0.0) {  // lanes that did not move keep their (s, c) bit for bit
+                s = s2;
+                c = c2;
+            }
+        }
+        if (!__any_sync(kFull, active)) break;
+    }
+    iters += it;
+    return rvl::kepler_rv(s, c, ec, A, Bs, Ce);
+}
+
+// ---- per-point setup: theta row -> per-warp constants (modelk :411-457, :181-192) ---------
+// lane p < K handles planet p; lane i < n_inst handles instrument i; lane 0 the drift/linpar
+// coefficients.  Returns (warp-uniform) whether the point is a valid Keplerian.
+__device__ __forceinline__ bool point_setup(const rvl_model_desc &m, const double *row,
+                                            double *wc, int lane)
+{
+    const int K = m.n_planets;
+    bool bad = false;
+    if (lane < K) {
+        const rvl_planet_desc &pl = m.planet[lane];
+        double amp = par_of(pl.amp, row);
+        if (pl.amp_is_log) amp = exp(amp);
+        double per = par_of(pl.period, row);
+        if (pl.period_is_log) per = exp(per);
+        const double a = par_of(pl.e1, row), b = par_of(pl.e2, row);
+        double ecc, omega;
+        if (pl.ecc_mode == RVL_ECC_SECOS_SESIN) {
+            ecc = rvl::add(rvl::mul(a, a), rvl::mul(b, b));
+            omega = atan2(b, a);
+            bad = ecc > 1.0;
+        } else if (pl.ecc_mode == RVL_ECC_ECOS_ESIN) {
+            ecc = sqrt(rvl::add(rvl::mul(a, a), rvl::mul(b, b)));
+            omega = atan2(b, a);
+            bad = ecc > 1.0;
+        } else {
+            ecc = a;
+            omega = b;
+        }
+        double M0 = par_of(pl.phase, row);
+        if (pl.phase_mode == RVL_PHASE_ML0) M0 = rvl::sub(M0, omega);
+        const double ec = ecc > 0.99 ? 0.99 : ecc;  // trueanomaly.c:11-12
+        double sw, cw;
+        sincos(omega, &sw, &cw);
+        const double root = sqrt(rvl::mul(rvl::sub(1.0, ec), rvl::add(1.0, ec)));
+        double *pc = wc + lane * kPlanetStride;
+        pc[0] = __ddiv_rn(6.283185307179586, per);  // 2*np.pi/P_day (:459)
+        pc[1] = M0;
+        pc[2] = ec;
+        pc[3] = rvl::mul(amp, cw);
+        pc[4] = -rvl::mul(rvl::mul(amp, sw), root);
+        pc[5] = rvl::mul(amp, rvl::mul(ecc, cw));
+        pc[6] = par_of(pl.epoch, row);
+    }
+    double *ic = wc + K * kPlanetStride;
+    if (lane < m.n_inst) {
+        ic[2 * lane] = par_of(m.offset[lane], row);
+        double j2 = 0.0;
+        if (m.jitter_in_model) {
+            const double j = par_of(m.jitter[lane], row);
+            j2 = rvl::mul(j, j);
+        }
+        ic[2 * lane + 1] = j2;
+    }
+    double *dc = ic + 2 * m.n_inst;
+    if (lane < 4) dc[lane] = m.drift_in_model ? par_of(m.drift[lane], row) : 0.0;
+    if (lane < m.n_linpar) dc[4 + lane] = par_of(m.linpar[lane], row);
+    __syncwarp();
+    return !__any_sync(kFull, bad);
+}
+
+// ---- the likelihood kernel ------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [0,8) mbarrier | [128, 128+sizeof(model)) model | epoch columns | inst ids | warp consts
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    rvl_model_desc *sm = reinterpret_cast<rvl_model_desc *>(smem_raw + 128);
+    const int sl = blockIdx.x % a.S;
+    const int Ctot = a.Npad / 32;
+    const int c0 = sl * a.cps;
+    const int nch = min(a.cps, Ctot - c0);  // chunks in this slice (>= 1 by construction)
+    const int ne = nch * 32;
+    double *scol = reinterpret_cast<double *>(smem_raw + 128 + kModelBytes);
+    uint8_t *sinst = reinterpret_cast<uint8_t *>(scol + (size_t)a.ncol * ne);
+    double *wconst = reinterpret_cast<double *>(
+        smem_raw + 128 + kModelBytes + (((size_t)a.ncol * ne * 8 + ne + 127) / 128) * 128);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned col_bytes = (unsigned)ne * 8u;
+        mbar_expect_tx(bar, col_bytes * (unsigned)a.ncol + (unsigned)ne);
+        for (int cidx = 0; cidx < a.ncol; ++cidx)
+            tma_load_1d(scol + (size_t)cidx * ne, a.cols + (size_t)cidx * a.Npad + (size_t)c0 * 32,
+                        col_bytes, bar);
+        tma_load_1d(sinst, a.inst + (size_t)c0 * 32, (unsigned)ne, bar);
+    }
+    // model description: plain cooperative copy (1.6 KB) while the TMA is in flight
+    {
+        const int nw = (int)(sizeof(rvl_model_desc) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.model);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sm);
+        for (int i = tid; i < nw; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const rvl_model_desc &m = *sm;
+    const int K = m.n_planets;
+    const double tol = m.tol;
+    const int itmax = m.itmax;
+    const bool has_drift = m.drift_in_model != 0;
+    const int nlin = m.n_linpar;
+    const double *s_t = scol, *s_rv = scol + ne, *s_s2 = scol + 2 * (size_t)ne;
+    const double *s_tt = scol + 3 * (size_t)ne;  // valid when has_drift
+    const double *s_lin = scol + (size_t)(3 + (has_drift ? 1 : 0)) * ne;
+    double *wc = wconst + (size_t)warp * a.wstride;
+    const double *ic = wc + K * kPlanetStride;
+    const double *dc = ic + 2 * m.n_inst;
+    const int e_base = c0 * 32;  // global epoch index of the slice start
+
+    unsigned long long tot_iters = 0, tot_caps = 0, tot_invalid = 0;
+
+    while (true) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(&a.work[sl], 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if ((long long)idx >= a.B) break;
+        const long long pt = idx;
+        const double *row = a.theta + pt * m.ndim;
+
+        __syncwarp();
+        const bool valid = point_setup(m, row, wc, lane);
+
+        double chi = 0.0, prod = 1.0;
+        int esum = 0, iters = 0, caps = 0;
+        bool ok = true;
+        if (valid) {
+            for (int ch = 0; ch < nch; ++ch) {
+                const int j = ch * 32 + lane;
+                const bool live = (e_base + j) < a.N;
+                const double t = s_t[j];
+                double rvsum = 0.0;
+                int it_l = 0, cap_l = 0;
+                for (int p = 0; p < K; ++p) {
+                    const double v = solve_planet<VARIANT>(t, wc + p * kPlanetStride, tol, itmax,
+                                                           it_l, cap_l);
+                    rvsum = (p == 0) ? v : rvl::add(rvsum, v);
+                }
+                if (live) {  // padded lanes of the last chunk re-solve the last epoch: not counted
+                    iters += it_l;
+                    caps += cap_l;
+                }
+                const int ii = sinst[j];
+                double rvm = ic[2 * ii];
+                if (K > 0) rvm = rvl::add(rvm, rvsum);
+                if (has_drift) {
+                    const double tt = s_tt[j];
+                    const double t2 = rvl::mul(tt, tt);
+                    double dr = rvl::mul(dc[0], tt);
+                    dr = rvl::add(dr, rvl::mul(dc[1], t2));
+                    dr = rvl::add(dr, rvl::mul(dc[2], rvl::mul(t2, tt)));
+                    dr = rvl::add(dr, rvl::mul(dc[3], rvl::mul(t2, t2)));
+                    rvm = rvl::add(rvm, dr);
+                }
+                for (int l = 0; l < nlin; ++l)
+                    rvm = rvl::add(rvm, rvl::mul(dc[4 + l], s_lin[(size_t)l * ne + j]));
+                const double res = rvl::sub(s_rv[j], rvm);
+                const double var = rvl::add(s_s2[j], ic[2 * ii + 1]);
+                double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
+                double mant;
+                int ex;
+                const bool okv = rvl::split_pos(var, mant, ex);
+                if (live) {
+                    chi = rvl::add(chi, term);
+                    prod = rvl::mul(prod, mant);
+                    esum += ex;
+                    ok = ok && okv;
+                }
+                if ((ch & 511) == 511) {  // keep the mantissa product inside the double range
+                    double mm;
+                    int ee;
+                    rvl::split_pos(prod, mm, ee);
+                    prod = mm;
+                    esum += ee;
+                }
+            }
+        }
+        // ---- slice reduction: chi^2 sum, mantissa product, exponent sum ----
+        double S1, S2;
+        if (valid) {
+            const bool all_ok = __all_sync(kFull, ok);
+            if (all_ok) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    chi = rvl::add(chi, __shfl_xor_sync(kFull, chi, o));
+                    if (o == 4) {  // 8 lanes x <=512 mantissas each can reach 2^1023: renormalise
+                        double mm;
+                        int ee;
+                        rvl::split_pos(prod, mm, ee);
+                        prod = mm;
+                        esum += ee;
+                    }
+                    prod = rvl::mul(prod, __shfl_xor_sync(kFull, prod, o));
+                    esum += __shfl_xor_sync(kFull, esum, o);
+                }
+                // sum ln sqrt(var) = 0.5 (ln prod + esum ln 2)
+                const double ld = rvl::fma_((double)esum, rvl::kLn2Hi,
+                                           rvl::fma_((double)esum, rvl::kLn2Lo, log(prod)));
+                S1 = rvl::mul(0.5, ld);
+            } else {
+                // a variance that is zero / subnormal / negative / non-finite: plain logs
+                double acc = 0.0;
+                for (int ch = 0; ch < nch; ++ch) {
+                    const int j = ch * 32 + lane;
+                    if ((e_base + j) < a.N) {
+                        const double var = rvl::add(s_s2[j], ic[2 * (int)sinst[j] + 1]);
+                        acc = rvl::add(acc, log(sqrt(var)));
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc = rvl::add(acc, __shfl_xor_sync(kFull, acc, o));
+                    chi = rvl::add(chi, __shfl_xor_sync(kFull, chi, o));
+                }
+                S1 = acc;
+            }
+            S2 = chi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                iters += __shfl_xor_sync(kFull, iters, o);
+                caps += __shfl_xor_sync(kFull, caps, o);
+            }
+            tot_iters += (unsigned long long)iters;
+            tot_caps += (unsigned long long)caps;
+        } else {
+            S1 = 0.0;
+            S2 = 0.0;
+            if (sl == 0) ++tot_invalid;
+        }
+        if (lane == 0) {
+            if (a.S == 1) {
+                // (cte - sum ln sqrt var) - sum r^2/(2 var)   (:80); invalid -> -1e30 (:203)
+                a.lnl[pt] = valid ? rvl::sub(rvl::sub(a.cte, S1), S2) : -1e30;
+            } else {
+                double *o = a.partial + ((size_t)pt * a.S + sl) * 2;
+                o[0] = S1;
+                o[1] = S2;
+                if (sl == 0) a.flags[pt] = valid ? 0 : 1;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (tot_iters) atomicAdd(&a.counters[0], tot_iters);
+        if (tot_caps) atomicAdd(&a.counters[1], tot_caps);
+        if (tot_invalid) atomicAdd(&a.counters[2], tot_invalid);
+    }
+}
+
+// combine the per-slice partial sums in slice order (deterministic)
+__global__ void combine_slices_kernel(const double *partial, const int *flags, double *lnl,
+                                      long long B, int S, double cte)
+{
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= B) return;
+    if (flags[pt]) {
+        lnl[pt] = -1e30;
+        return;
+    }
+    const double *p = partial + (size_t)pt * S * 2;
+    double s1 = 0.0, s2 = 0.0;
+    for (int s = 0; s < S; ++s) {
+        s1 = rvl::add(s1, p[2 * s]);
+        s2 = rvl::add(s2, p[2 * s + 1]);
+    }
+    lnl[pt] = rvl::sub(rvl::sub(cte, s1), s2);
+}
+
+// ---- prior transform: unit cube -> theta (evidence/ultranest/__init__.py:125-137) -----------
+__device__ __forceinline__ double ppf_eval(const rvl_prior_desc &pr, const double *tables,
+                                           double q)
+{
+    const double p0 = pr.p[0], p1 = pr.p[1];
+    switch (pr.kind) {
+    case RVL_PRIOR_UNIFORM:  // priors.py:41-42
+        return rvl::add(p0, rvl::mul(rvl::sub(p1, p0), q));
+    case RVL_PRIOR_JEFFREYS:  // :62-63
+        return rvl::mul(p0, pow(__ddiv_rn(p1, p0), q));
+    case RVL_PRIOR_MODJEFFREYS:  // :82-83
+        return rvl::sub(rvl::mul(p0, pow(rvl::add(1.0, __ddiv_rn(p1, p0)), q)), p0);
+    case RVL_PRIOR_UNIFORMFREQ:  // :100-101   xmin / (1 - q*(xmax-xmin)/xmax)
+        return __ddiv_rn(p0, rvl::sub(1.0, __ddiv_rn(rvl::mul(q, rvl::sub(p1, p0)), p1)));
+    case RVL_PRIOR_TRUNCRAYLEIGH: {  // :249-252
+        const double s2 = rvl::mul(p0, p0);
+        const double A = rvl::sub(1.0, exp(-__ddiv_rn(rvl::mul(p1, p1), rvl::mul(2.0, s2))));
+        return sqrt(rvl::mul(rvl::mul(-2.0, s2), log(rvl::sub(1.0, rvl::mul(q, A)))));
+    }
+    case RVL_PRIOR_NORMAL:  // scipy.stats.norm(loc, scale).ppf
+        return rvl::add(rvl::mul(normcdfinv(q), p1), p0);
+    case RVL_PRIOR_LOGNORMAL:  // scipy.stats.lognorm(s, loc, scale).ppf
+        return rvl::add(rvl::mul(exp(rvl::mul(p0, normcdfinv(q))), pr.p[2]), p1);
+    case RVL_PRIOR_TABLE: {
+        // interp1d(cdf, x)(q): hi = clip(searchsorted(cdf, q, 'left'), 1, len-1)
+        const double *cdf = tables + pr.table_offset;
+        const double *x = cdf + pr.table_len;
+        int lo = 0, hi = pr.table_len;
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if (__ldg(cdf + mid) < q) lo = mid + 1; else hi = mid;
+        }
+        int k = max(1, min(pr.table_len - 1, lo));
+        const double x0 = __ldg(x + k - 1), x1 = __ldg(x + k);
+        const double c0 = __ldg(cdf + k - 1), c1 = __ldg(cdf + k);
+        const double slope = __ddiv_rn(rvl::sub(x1, x0), rvl::sub(c1, c0));
+        const double y = rvl::add(rvl::mul(slope, rvl::sub(q, c0)), x0);
+        return p0 != 0.0 ? exp10(y) : y;  // p0 = 1: Log10Normal, 10**interp (priors.py:144)
+    }
+    default:
+        return nan("");
+    }
+}
+
+__global__ void prior_transform_kernel(const rvl_prior_desc *priors, const double *tables,
+                                       const double *U, double *Theta, long long total, int ndim)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int col = (int)(i % ndim);
+    Theta[i] = ppf_eval(priors[col], tables, U[i]);
+}
+
+// ---- the reference's native FFI on the device (trueanomaly.h:4) --------------------------------
+__global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *nu, int itmax,
+                                   double tol, int *caphit)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ii = min(i, n - 1);  // whole warps stay converged; extra lanes duplicate the last
+    const double ec = ecc > 0.99 ? 0.99 : ecc;
+    const double m = __ldg(M + ii);
+    double E = m, s, c;
+    sincos_any(E, s, c);
+    bool active = true;
+    int it = 0, cap = 0;
+    while (true) {
+        double d = 0.0;
+        if (active) {
+            double En;
+            d = rvl::newton_step(E, s, c, m, ec, En);
+            E = En;
+            ++it;
+            if (it >= itmax) { active = false; cap = 1; }
+            else if (!(fabs(d) > tol)) active = false;
+        }
+        const double ad = fabs(d);
+        if (__all_sync(kFull, ad <= rvl::kTinyStep)) rvl::advance_tiny(d, s, c);
+        else if (__all_sync(kFull, ad <= rvl::kSmallStep)) rvl::advance_small(d, s, c);
+        else {
+            double s2, c2;
+            sincos_any(E, s2, c2);
+            if (d != 0.0) { s = s2; c = c2; }
+        }
+        if (!__any_sync(kFull, active)) break;
+    }
+    if (i < n) {
+        // nu = 2 atan(sqrt((1+e)/(1-e)) tan(E/2))  ==  atan2(sqrt(1-e^2) sin E, cos E - e)
+        const double root = sqrt(rvl::mul(rvl::sub(1.0, ec), rvl::add(1.0, ec)));
+        nu[i] = atan2(rvl::mul(root, s), rvl::sub(c, ec));
+        if (cap) atomicExch(caphit, 1);
+    }
+}
+
+// ---- register-resident DFMA loop: the FP64 roofline denominator -------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b);
+            x3 = __fma_rn(x3, a, b); x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b);
+            x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+// =================================================================================================
+// handle + C-ABI
+// =================================================================================================
+struct rvl_handle {
+    int device = 0;
+    int sm_count = 0, smem_optin = 0, clock_khz = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // host copies of the staged inputs
+    int N = 0, Npad = 0, n_inst = 0;
+    std::vector<double> h_t, h_rv, h_err;
+    std::vector<int32_t> h_inst;
+    std::vector<double> h_linpar[RVL_MAX_LINPAR];
+    bool have_data = false, have_model = false, have_priors = false, cols_dirty = true;
+    rvl_model_desc model{};
+
+    // device
+    double *d_cols = nullptr;
+    uint8_t *d_inst = nullptr;
+    int ncol = 0;
+    rvl_model_desc *d_model = nullptr;
+    rvl_prior_desc *d_priors = nullptr;
+    double *d_tables = nullptr;
+    int prior_ndim = 0;
+
+    // per-call scratch (grown on demand)
+    long long cap_B = 0, cap_flags = 0;
+    size_t cap_partial = 0;
+    double *d_theta = nullptr, *d_u = nullptr, *d_lnl = nullptr, *d_partial = nullptr;
+    int *d_flags = nullptr;
+    unsigned long long *d_counters = nullptr;  // 3
+    unsigned int *d_work = nullptr;            // sm_count
+
+    // options
+    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1;
+
+    // bookkeeping
+    uint64_t n_points = 0, n_solves = 0, launches = 0;
+    double last_ms = 0.0;
+    bool timing_pending = false;
+};
+
+namespace {
+
+int fail(rvl_t *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(h, RVL_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// build the epoch columns in HBM: t, vrad, svrad^2, [(t-tref)/365.25], [linpar...], inst ids
+int upload_columns(rvl_t *h)
+{
+    const int N = h->N, Npad = h->Npad;
+    const bool drift = h->have_model && h->model.drift_in_model;
+    const int nlin = h->have_model ? h->model.n_linpar : 0;
+    const int ncol = 3 + (drift ? 1 : 0) + nlin;
+    for (int l = 0; l < nlin; ++l)
+        if ((int)h->h_linpar[l].size() != N)
+            return fail(h, RVL_ESTATE, "linear-parameter column " + std::to_string(l) + " not set");
+    std::vector<double> cols((size_t)ncol * Npad);
+    std::vector<uint8_t> ids((size_t)Npad);
+    for (int j = 0; j < Npad; ++j) {
+        const int k = j < N ? j : N - 1;  // padding duplicates the last epoch (masked in-kernel)
+        cols[j] = h->h_t[k];
+        cols[(size_t)Npad + j] = h->h_rv[k];
+        cols[(size_t)2 * Npad + j] = h->h_err[k] * h->h_err[k];  // svrad**2 (:190-192)
+        int c = 3;
+        if (drift) cols[(size_t)(c++) * Npad + j] = (h->h_t[k] - h->model.tref) / 365.25;  // :270
+        for (int l = 0; l < nlin; ++l) cols[(size_t)(c++) * Npad + j] = h->h_linpar[l][k];
+        ids[j] = (uint8_t)h->h_inst[k];
+    }
+    if (h->d_cols) cudaFree(h->d_cols);
+    if (h->d_inst) cudaFree(h->d_inst);
+    h->d_cols = nullptr; h->d_inst = nullptr;
+    CU(h, cudaMalloc(&h->d_cols, cols.size() * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_inst, ids.size()));
+    CU(h, cudaMemcpy(h->d_cols, cols.data(), cols.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->d_inst, ids.data(), ids.size(), cudaMemcpyHostToDevice));
+    h->ncol = ncol;
+    h->cols_dirty = false;
+    return RVL_OK;
+}
+
+// device staging for the host-buffer entry points
+int ensure_io(rvl_t *h, long long B)
+{
+    if (B <= h->cap_B) return RVL_OK;
+    const long long cap = std::max<long long>(B, 1024);
+    cudaFree(h->d_theta); cudaFree(h->d_u); cudaFree(h->d_lnl);
+    h->d_theta = h->d_u = h->d_lnl = nullptr;
+    h->cap_B = 0;
+    const size_t row = (size_t)std::max(1, std::max(h->model.ndim, h->prior_ndim));
+    CU(h, cudaMalloc(&h->d_theta, (size_t)cap * row * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_u, (size_t)cap * row * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_lnl, (size_t)cap * sizeof(double)));
+    h->cap_B = cap;
+    return RVL_OK;
+}
+
+// per-slice partial sums (only when the epoch axis is cut into S > 1 slices)
+int ensure_partial(rvl_t *h, long long B, int S)
+{
+    if (S <= 1) return RVL_OK;
+    const size_t need = (size_t)B * S;
+    if (need <= h->cap_partial && B <= h->cap_flags) return RVL_OK;
+    cudaFree(h->d_partial); cudaFree(h->d_flags);
+    h->d_partial = nullptr; h->d_flags = nullptr;
+    h->cap_partial = 0; h->cap_flags = 0;
+    CU(h, cudaMalloc(&h->d_partial, need * 2 * sizeof(double)));
+    CU(h, cudaMalloc(&h->d_flags, (size_t)B * sizeof(int)));
+    h->cap_partial = need; h->cap_flags = B;
+    return RVL_OK;
+}
+
+struct Plan {
+    int S, cps, W, grid, wstride;
+    size_t smem;
+};
+
+size_t smem_need(int ncol, int ne, int W, int wstride)
+{
+    return 128 + kModelBytes + (((size_t)ncol * ne * 8 + ne + 127) / 128) * 128 +
+           (size_t)W * wstride * 8;
+}
+
+int make_plan(rvl_t *h, long long B, Plan &pl)
+{
+    const rvl_model_desc &m = h->model;
+    const int Ctot = h->Npad / 32;
+    int wstride = m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar;
+    wstride = (wstride + 1) & ~1;
+    int W = h->opt_warps > 0 ? h->opt_warps : 32;
+    W = std::max(1, std::min(32, W));
+    // smallest slice count whose slice fits in shared memory
+    int S = 1;
+    auto fits = [&](int s) {
+        const int cps = (Ctot + s - 1) / s;
+        return smem_need(h->ncol, cps * 32, W, wstride) <= (size_t)h->smem_optin;
+    };
+    while (S < Ctot && !fits(S)) ++S;
+    if (!fits(S)) return fail(h, RVL_EINVAL, "epoch chunk does not fit in shared memory");
+    if (h->opt_slices > 0) {
+        S = std::max(S, std::min(h->opt_slices, Ctot));
+    } else {
+        // small batches: cut epochs finer so that every warp of the chip gets >= ~4 work items,
+        // but keep >= 8 chunks per slice so the per-point setup stays amortised
+        const long long warps_total = (long long)h->sm_count * W;
+        long long want = (4 * warps_total + B - 1) / std::max<long long>(B, 1);
+        const int maxS = std::max(1, Ctot / 8);
+        S = std::max<long long>(S, std::min<long long>(want, maxS));
+    }
+    S = std::min(S, h->sm_count);
+    int cps = (Ctot + S - 1) / S;
+    S = (Ctot + cps - 1) / cps;  // drop empty trailing slices
+    if (!fits(S)) return fail(h, RVL_EINVAL, "slice does not fit in shared memory");
+    pl.S = S; pl.cps = cps; pl.W = W; pl.wstride = wstride;
+    pl.grid = std::max(1, h->sm_count / S) * S;
+    pl.smem = smem_need(h->ncol, cps * 32, W, wstride);
+    return RVL_OK;
+}
+
+template <int V>
+int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
+{
+    CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               h->smem_optin));
+    rv_lnl_kernel<V><<<pl.grid, pl.W * 32, pl.smem, st>>>(a);
+    CU(h, cudaGetLastError());
+    return RVL_OK;
+}
+
+// enqueue: zero work counters, likelihood kernel, (combine).  dTheta/dlnL are device pointers.
+int enqueue_loglike(rvl_t *h, const double *dTheta, long long B, double *dlnL, cudaStream_t st,
+                    bool timed)
+{
+    if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
+    if (h->cols_dirty) { int rc = upload_columns(h); if (rc) return rc; }
+    if (B <= 0) return RVL_OK;
+    if (B > 0xfffffff0LL) return fail(h, RVL_EINVAL, "batch too large for one call (max ~4.29e9)");
+    Plan pl;
+    int rc = make_plan(h, B, pl);
+    if (rc) return rc;
+    rc = ensure_partial(h, B, pl.S);
+    if (rc) return rc;
+    KArgs a{};
+    a.model = h->d_model; a.cols = h->d_cols; a.inst = h->d_inst; a.theta = dTheta; a.lnl = dlnL;
+    a.partial = h->d_partial; a.flags = h->d_flags; a.counters = h->d_counters; a.work = h->d_work;
+    a.B = B; a.cte = -0.5 * h->N * log(2 * M_PI); a.N = h->N; a.Npad = h->Npad; a.ncol = h->ncol;
+    a.S = pl.S; a.cps = pl.cps; a.wstride = pl.wstride;
+    CU(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned) * (size_t)h->sm_count, st));
+    if (timed) CU(h, cudaEventRecord(h->ev0, st));
+    rc = h->opt_variant == 1 ? launch_lnl_v<1>(h, a, pl, st) : launch_lnl_v<0>(h, a, pl, st);
+    if (rc) return rc;
+    if (timed) { CU(h, cudaEventRecord(h->ev1, st)); h->timing_pending = true; }
+    ++h->launches;
+    if (pl.S > 1) {
+        const int tb = 256;
+        combine_slices_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(h->d_partial, h->d_flags,
+                                                                         dlnL, B, pl.S, a.cte);
+        CU(h, cudaGetLastError());
+        ++h->launches;
+    }
+    h->n_points += (uint64_t)B;
+    h->n_solves += (uint64_t)B * (uint64_t)h->N * (uint64_t)h->model.n_planets;
+    return RVL_OK;
+}
+
+int enqueue_transform(rvl_t *h, const double *dU, long long B, double *dTheta, cudaStream_t st)
+{
+    if (!h->have_priors) return fail(h, RVL_ESTATE, "set priors first");
+    if (B <= 0) return RVL_OK;
+    const long long total = B * h->prior_ndim;
+    const int tb = 256;
+    prior_transform_kernel<<<(unsigned)((total + tb - 1) / tb), tb, 0, st>>>(
+        h->d_priors, h->d_tables, dU, dTheta, total, h->prior_ndim);
+    CU(h, cudaGetLastError());
+    ++h->launches;
+    return RVL_OK;
+}
+
+int finish_timing(rvl_t *h)
+{
+    if (h->timing_pending) {
+        float ms = 0.f;
+        CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_ms = ms;
+        h->timing_pending = false;
+    }
+    return RVL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvl_abi_version(void) { return RVL_ABI_VERSION; }
+
+int rvl_create(rvl_t **out, int device)
+{
+    if (!out) return fail(nullptr, RVL_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RVL_ENODEV,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                        " (librvlnl has no CPU fallback)");
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= ndev) return fail(nullptr, RVL_ENODEV, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, RVL_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, RVL_ENODEV,
+                    "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                        "; librvlnl is built for sm_100a only");
+    rvl_t *h = new (std::nothrow) rvl_handle();
+    if (!h) return fail(nullptr, RVL_ENOMEM, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->clock_khz = prop.clockRate;
+    DevGuard g(device);
+    auto bail = [&](const char *what, cudaError_t ce) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(ce);
+        rvl_destroy(h);
+        return fail(nullptr, RVL_ECUDA, msg);
+    };
+    cudaError_t ce;
+    if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
+    if ((ce = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("event", ce);
+    if ((ce = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("event", ce);
+    if ((ce = cudaMalloc(&h->d_counters, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail("malloc", ce);
+    if ((ce = cudaMemset(h->d_counters, 0, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail("memset", ce);
+    if ((ce = cudaMalloc(&h->d_work, sizeof(unsigned) * (size_t)h->sm_count)) != cudaSuccess) return bail("malloc", ce);
+    if ((ce = cudaMalloc(&h->d_model, sizeof(rvl_model_desc))) != cudaSuccess) return bail("malloc", ce);
+    *out = h;
+    return RVL_OK;
+}
+
+void rvl_destroy(rvl_t *h)
+{
+    if (!h) return;
+    DevGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_cols); cudaFree(h->d_inst); cudaFree(h->d_model); cudaFree(h->d_priors);
+    cudaFree(h->d_tables); cudaFree(h->d_theta); cudaFree(h->d_u); cudaFree(h->d_lnl);
+    cudaFree(h->d_partial); cudaFree(h->d_flags); cudaFree(h->d_counters); cudaFree(h->d_work);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *rvl_last_error(const rvl_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rvl_set_data(rvl_t *h, const double *t, const double *rv, const double *err,
+                 const int32_t *inst, int32_t n, int32_t n_inst)
+{
+    if (!h) return RVL_EINVAL;
+    if (!t || !rv || !err || !inst) return fail(h, RVL_EINVAL, "NULL data pointer");
+    if (n <= 0) return fail(h, RVL_EINVAL, "n must be positive");
+    if (n_inst <= 0 || n_inst > RVL_MAX_INST)
+        return fail(h, RVL_EINVAL, "n_inst must be in [1, " + std::to_string(RVL_MAX_INST) + "]");
+    for (int j = 0; j < n; ++j)
+        if (inst[j] < 0 || inst[j] >= n_inst) return fail(h, RVL_EINVAL, "instrument id out of range");
+    h->N = n; h->Npad = (n + 31) / 32 * 32; h->n_inst = n_inst;
+    h->h_t.assign(t, t + n); h->h_rv.assign(rv, rv + n); h->h_err.assign(err, err + n);
+    h->h_inst.assign(inst, inst + n);
+    for (auto &c : h->h_linpar) c.clear();
+    h->have_data = true; h->cols_dirty = true;
+    return RVL_OK;
+}
+
+int rvl_set_linpar(rvl_t *h, int32_t idx, const double *col, int32_t n)
+{
+    if (!h) return RVL_EINVAL;
+    if (!h->have_data) return fail(h, RVL_ESTATE, "set data first");
+    if (idx < 0 || idx >= RVL_MAX_LINPAR || !col || n != h->N)
+        return fail(h, RVL_EINVAL, "bad linear-parameter column");
+    h->h_linpar[idx].assign(col, col + n);
+    h->cols_dirty = true;
+    return RVL_OK;
+}
+
+static bool param_ok(const rvl_param &p, int ndim) { return p.slot >= -1 && p.slot < ndim; }
+
+int rvl_set_model(rvl_t *h, const rvl_model_desc *d)
+{
+    if (!h) return RVL_EINVAL;
+    if (!d) return fail(h, RVL_EINVAL, "desc is NULL");
+    if (d->abi_version != RVL_ABI_VERSION) return fail(h, RVL_EINVAL, "abi_version mismatch");
+    if (d->ndim < 0 || d->ndim > RVL_MAX_DIM) return fail(h, RVL_EINVAL, "ndim out of range");
+    if (d->n_planets < 0 || d->n_planets > RVL_MAX_PLANETS) return fail(h, RVL_EINVAL, "n_planets out of range");
+    if (d->n_inst <= 0 || d->n_inst > RVL_MAX_INST) return fail(h, RVL_EINVAL, "n_inst out of range");
+    if (d->n_linpar < 0 || d->n_linpar > RVL_MAX_LINPAR) return fail(h, RVL_EINVAL, "n_linpar out of range");
+    if (h->have_data && d->n_inst != h->n_inst) return fail(h, RVL_EINVAL, "n_inst differs from the staged data");
+    if (d->itmax < 1) return fail(h, RVL_EINVAL, "itmax must be >= 1");
+    if (!(d->tol > 0)) return fail(h, RVL_EINVAL, "tol must be positive");
+    for (int p = 0; p < d->n_planets; ++p) {
+        const rvl_planet_desc &pl = d->planet[p];
+        if (!param_ok(pl.amp, d->ndim) || !param_ok(pl.period, d->ndim) || !param_ok(pl.e1, d->ndim) ||
+            !param_ok(pl.e2, d->ndim) || !param_ok(pl.phase, d->ndim) || !param_ok(pl.epoch, d->ndim))
+            return fail(h, RVL_EINVAL, "planet parameter slot out of range");
+        if (pl.ecc_mode < 0 || pl.ecc_mode > 2 || pl.phase_mode < 0 || pl.phase_mode > 1)
+            return fail(h, RVL_EINVAL, "bad parametrisation enum");
+    }
+    for (int i = 0; i < d->n_inst; ++i)
+        if (!param_ok(d->offset[i], d->ndim) || !param_ok(d->jitter[i], d->ndim))
+            return fail(h, RVL_EINVAL, "instrument parameter slot out of range");
+    for (int i = 0; i < 4; ++i)
+        if (!param_ok(d->drift[i], d->ndim)) return fail(h, RVL_EINVAL, "drift slot out of range");
+    for (int i = 0; i < d->n_linpar; ++i)
+        if (!param_ok(d->linpar[i], d->ndim)) return fail(h, RVL_EINVAL, "linpar slot out of range");
+    DevGuard g(h->device);
+    h->model = *d;
+    CU(h, cudaMemcpy(h->d_model, d, sizeof(*d), cudaMemcpyHostToDevice));
+    h->have_model = true; h->cols_dirty = true;
+    // scratch rows depend on ndim
+    h->cap_B = 0;
+    return RVL_OK;
+}
+
+int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const double *tables,
+                   int64_t n_table_doubles)
+{
+    if (!h) return RVL_EINVAL;
+    if (!priors || ndim <= 0 || ndim > RVL_MAX_DIM) return fail(h, RVL_EINVAL, "bad priors / ndim");
+    for (int i = 0; i < ndim; ++i) {
+        const rvl_prior_desc &p = priors[i];
+        if (p.kind < 0 || p.kind > RVL_PRIOR_TABLE) return fail(h, RVL_EINVAL, "unknown prior kind");
+        if (p.kind == RVL_PRIOR_TABLE &&
+            (p.table_len < 2 || p.table_offset < 0 || !tables ||
+             p.table_offset + 2LL * p.table_len > n_table_doubles))
+            return fail(h, RVL_EINVAL, "prior table out of bounds");
+    }
+    DevGuard g(h->device);
+    cudaFree(h->d_priors); cudaFree(h->d_tables);
+    h->d_priors = nullptr; h->d_tables = nullptr;
+    CU(h, cudaMalloc(&h->d_priors, sizeof(rvl_prior_desc) * (size_t)ndim));
+    CU(h, cudaMemcpy(h->d_priors, priors, sizeof(rvl_prior_desc) * (size_t)ndim, cudaMemcpyHostToDevice));
+    if (n_table_doubles > 0 && tables) {
+        CU(h, cudaMalloc(&h->d_tables, sizeof(double) * (size_t)n_table_doubles));
+        CU(h, cudaMemcpy(h->d_tables, tables, sizeof(double) * (size_t)n_table_doubles, cudaMemcpyHostToDevice));
+    }
+    h->prior_ndim = ndim; h->have_priors = true;
+    h->cap_B = 0;
+    return RVL_OK;
+}
+
+int rvl_set_option(rvl_t *h, const char *name, int64_t value)
+{
+    if (!h || !name) return RVL_EINVAL;
+    const std::string n(name);
+    if (n == "variant") { if (value < 0 || value > 1) return fail(h, RVL_EINVAL, "variant in {0,1}"); h->opt_variant = (int)value; }
+    else if (n == "slices") h->opt_slices = (int)std::max<int64_t>(0, value);
+    else if (n == "warps") h->opt_warps = (int)std::max<int64_t>(0, std::min<int64_t>(32, value));
+    else if (n == "timing") h->opt_timing = value != 0;
+    else return fail(h, RVL_EINVAL, "unknown option " + n);
+    return RVL_OK;
+}
+
+int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, void *stream)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    DevGuard g(h->device);
+    return enqueue_loglike(h, dTheta, B, dlnL, (cudaStream_t)stream, h->opt_timing != 0);
+}
+
+int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!dU || !dTheta))) return fail(h, RVL_EINVAL, "bad arguments");
+    DevGuard g(h->device);
+    return enqueue_transform(h, dU, B, dTheta, (cudaStream_t)stream);
+}
+
+int rvl_transform_loglike_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, double *dlnL,
+                              void *stream)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!dU || !dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (h->have_model && h->have_priors && h->prior_ndim != h->model.ndim)
+        return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
+    DevGuard g(h->device);
+    int rc = enqueue_transform(h, dU, B, dTheta, (cudaStream_t)stream);
+    if (rc) return rc;
+    return enqueue_loglike(h, dTheta, B, dlnL, (cudaStream_t)stream, h->opt_timing != 0);
+}
+
+int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!Theta || !lnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
+    if (B == 0) return RVL_OK;
+    DevGuard g(h->device);
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
+    if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
+    rc = enqueue_loglike(h, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return finish_timing(h);
+}
+
+int rvl_transform(rvl_t *h, const double *U, int64_t B, double *Theta)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!U || !Theta))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->have_priors) return fail(h, RVL_ESTATE, "set priors first");
+    if (B == 0) return RVL_OK;
+    DevGuard g(h->device);
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
+    CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
+    rc = enqueue_transform(h, h->d_u, B, h->d_theta, h->stream);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return RVL_OK;
+}
+
+int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, double *lnL)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!U || !lnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->have_data || !h->have_model || !h->have_priors)
+        return fail(h, RVL_ESTATE, "set data, model and priors first");
+    if (h->prior_ndim != h->model.ndim) return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
+    if (B == 0) return RVL_OK;
+    DevGuard g(h->device);
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
+    CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
+    rc = enqueue_transform(h, h->d_u, B, h->d_theta, h->stream);
+    if (rc) return rc;
+    rc = enqueue_loglike(h, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
+    if (rc) return rc;
+    if (Theta) CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return finish_timing(h);
+}
+
+int rvl_trueanomaly(rvl_t *h, const double *M, int32_t n, double ecc, double *nu,
+                    int32_t niterationmax, double tol)
+{
+    if (!h) return RVL_EINVAL;
+    if (n < 0 || (n > 0 && (!M || !nu)) || niterationmax < 1) return fail(h, RVL_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    DevGuard g(h->device);
+    double *dM = nullptr, *dnu = nullptr;
+    int *dcap = nullptr;
+    CU(h, cudaMalloc(&dM, sizeof(double) * (size_t)n));
+    CU(h, cudaMalloc(&dnu, sizeof(double) * (size_t)n));
+    CU(h, cudaMalloc(&dcap, sizeof(int)));
+    CU(h, cudaMemsetAsync(dcap, 0, sizeof(int), h->stream));
+    CU(h, cudaMemcpyAsync(dM, M, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    const int tb = 128;
+    trueanomaly_kernel<<<(n + tb - 1) / tb, tb, 0, h->stream>>>(dM, n, ecc, dnu, niterationmax, tol, dcap);
+    ++h->launches;
+    int cap = 0;
+    cudaError_t e1 = cudaGetLastError();
+    cudaMemcpyAsync(nu, dnu, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&cap, dcap, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(dM); cudaFree(dnu); cudaFree(dcap);
+    if (e1 != cudaSuccess) return fail(h, RVL_ECUDA, cudaGetErrorString(e1));
+    if (e2 != cudaSuccess) return fail(h, RVL_ECUDA, cudaGetErrorString(e2));
+    return cap ? -1 : 0;  // same 0 / -1 convention as trueanomaly.c:32-40
+}
+
+int rvl_counters(rvl_t *h, rvl_counters_t *out)
+{
+    if (!h || !out) return RVL_EINVAL;
+    DevGuard g(h->device);
+    unsigned long long c[3] = {0, 0, 0};
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    out->n_points = h->n_points; out->n_solves = h->n_solves;
+    out->n_newton_iters = c[0]; out->n_cap_hits = c[1]; out->n_invalid = c[2];
+    return RVL_OK;
+}
+
+int rvl_reset_counters(rvl_t *h)
+{
+    if (!h) return RVL_EINVAL;
+    DevGuard g(h->device);
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemset(h->d_counters, 0, 3 * sizeof(unsigned long long)));
+    h->n_points = 0; h->n_solves = 0;
+    return RVL_OK;
+}
+
+int rvl_last_kernel_ms(rvl_t *h, double *ms)
+{
+    if (!h || !ms) return RVL_EINVAL;
+    if (h->timing_pending) {  // *_dev launches: wait for the kernel's end event
+        DevGuard g(h->device);
+        CU(h, cudaEventSynchronize(h->ev1));
+        int rc = finish_timing(h);
+        if (rc) return rc;
+    }
+    *ms = h->last_ms;
+    return RVL_OK;
+}
+
+int rvl_launch_count(rvl_t *h, uint64_t *n)
+{
+    if (!h || !n) return RVL_EINVAL;
+    *n = h->launches;
+    return RVL_OK;
+}
+
+int rvl_fp64_peak(rvl_t *h, double *tflops)
+{
+    if (!h || !tflops) return RVL_EINVAL;
+    DevGuard g(h->device);
+    const int blocks = h->sm_count * 8, tb = 256, iters = 4096;
+    double *out = nullptr;
+    CU(h, cudaMalloc(&out, sizeof(double) * (size_t)blocks * tb));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(h, cudaEventRecord(h->ev0, h->stream));
+        dfma_peak_kernel<<<blocks, tb, 0, h->stream>>>(out, iters, 0.999999, 1e-9);
+        CU(h, cudaEventRecord(h->ev1, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        ++h->launches;
+        float ms = 0.f;
+        CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * tb;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaFree(out);
+    *tflops = best;
+    return RVL_OK;
+}
+
+int rvl_device_info(rvl_t *h, int32_t *sm_count, int32_t *smem_optin, int32_t *clock_khz)
+{
+    if (!h) return RVL_EINVAL;
+    if (sm_count) *sm_count = h->sm_count;
+    if (smem_optin) *smem_optin = h->smem_optin;
+    if (clock_khz) *clock_khz = h->clock_khz;
+    return RVL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""
+Multi-GPU sharding of the likelihood batch: one process per GPU (``torch.distributed``), rows of
+theta split into contiguous blocks, per-rank lnL vectors gathered with one all-gather
+(NCCL over NVLink on the GPU box; gloo on CPU for the host-logic tests).
+
+The path has no other exchange step: every parameter vector's lnL depends only on its own row and
+on the small, replicated epoch data.  Rank r owns rows
+``[r*ceil(B/R), min(B, (r+1)*ceil(B/R)))``; the tail is padded so that the collective has equal
+counts on every rank.
+"""
+import math
+
+import numpy as np
+
+
+def shard_bounds(B, world_size, rank):
+    """Row block of ``rank``: (lo, hi, per) with per = ceil(B / world_size)."""
+    per = int(math.ceil(B / world_size)) if B > 0 else 0
+    lo = min(B, rank * per)
+    hi = min(B, lo + per)
+    return lo, hi, per
+
+
+class ShardedLikelihood:
+    """
+    Wraps a per-rank evaluator ``local_eval(theta_block) -> lnL_block`` (on the GPU box:
+    ``RVModel.log_likelihood_device`` on this rank's device) and presents the whole-batch call
+    a sampler makes: every rank passes the same ``theta[B, ndim]`` and receives the full
+    ``lnL[B]``.
+    """
+
+    def __init__(self, local_eval, ndim, device=None, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.local_eval = local_eval
+        self.ndim = ndim
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device
+
+    def __call__(self, theta):
+        """theta: torch tensor [B, ndim] (float64, on ``device``), identical on every rank."""
+        import torch
+        B = theta.shape[0]
+        lo, hi, per = shard_bounds(B, self.world, self.rank)
+        local = torch.full((per,), float("nan"), dtype=torch.float64, device=theta.device)
+        if hi > lo:
+            local[: hi - lo] = self.local_eval(theta[lo:hi].contiguous())
+        if self.world == 1:
+            return local[:B]
+        out = torch.empty(per * self.world, dtype=torch.float64, device=theta.device)
+        self.dist.all_gather_into_tensor(out, local, group=self.group)
+        return out[:B]
+
+    def evaluate_local(self, theta_block):
+        """Weak-scaling use (bench, parameter sweeps): this rank's own block, then the gather."""
+        import torch
+        local = self.local_eval(theta_block)
+        if self.world == 1:
+            return local
+        out = torch.empty(local.numel() * self.world, dtype=torch.float64, device=local.device)
+        self.dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+
+def split_rows(theta, world_size):
+    """Host-side helper: the list of row blocks the ranks own (for tests / CPU tools)."""
+    theta = np.asarray(theta)
+    B = theta.shape[0]
+    return [theta[slice(*shard_bounds(B, world_size, r)[:2])] for r in range(world_size)]

@@ -1,0 +1,194 @@
+/*
+ * rvlnl.h — C-ABI of librvlnl.so: the B200-native batched Keplerian
+ * radial-velocity log-likelihood and unit-cube prior transform.
+ *
+ * This is the drop-in boundary for the likelihood hot path of the `evidence`
+ * package.  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference checkout):
+ *
+ *   evidence/rvmodel/trueanomaly.h:4          int trueanomaly(double*,int,double,double*,int,double)
+ *   evidence/rvmodel/__init__.py:157-219      RVModel.log_likelihood(x)
+ *   evidence/rvmodel/__init__.py:59-80        BaseModel.logL(residuals, var)
+ *   evidence/rvmodel/__init__.py:222-273      RVModel.drift
+ *   evidence/rvmodel/__init__.py:343-463      RVModel.kep_rv / modelk
+ *   evidence/ultranest/__init__.py:125-146    prior(hypercube) / loglike(x) closures
+ *   evidence/polychord/__init__.py:130-171    prior(hypercube) / loglike(x) closures
+ *   evidence/priors.py:41-42,62-63,82-83,100-101,249-252  closed-form ppf
+ *
+ * Conventions
+ *   - plain C types only; caller owns every host buffer; the library owns all
+ *     device memory.  Row-major, C-contiguous float64.
+ *   - theta rows are in the model's SORTED-parnames column order
+ *     (evidence/rvmodel/__init__.py:43).
+ *   - return 0 on success, a negative RVL_E* code on failure; the message is
+ *     available from rvl_last_error().  Nothing throws across the ABI.
+ *   - an invalid Keplerian (e > 1 in the secos/sesin and ecos/esin
+ *     parametrisations) is DATA, not an error: lnL = -1e30
+ *     (evidence/rvmodel/__init__.py:198-203).
+ *   - host-buffer calls are synchronous (stream synchronised on return), like
+ *     the blocking callbacks of UltraNest / PolyChord.  The *_dev variants take
+ *     device pointers and a cudaStream_t (passed as void*) and are asynchronous.
+ *   - one handle per host thread.  There is no CPU fallback: every compute
+ *     entry point fails with RVL_ENODEV when no sm_100 device is usable.
+ */
+#ifndef RVLNL_H
+#define RVLNL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVL_ABI_VERSION 1
+
+#define RVL_MAX_PLANETS 8
+#define RVL_MAX_INST 16
+#define RVL_MAX_LINPAR 8
+#define RVL_MAX_DIM 128
+
+/* error codes */
+#define RVL_OK 0
+#define RVL_EINVAL (-1)  /* bad argument / inconsistent description        */
+#define RVL_ENODEV (-2)  /* no usable CUDA device                          */
+#define RVL_ECUDA (-3)   /* CUDA runtime error (see rvl_last_error)        */
+#define RVL_ESTATE (-4)  /* call order: data/model/priors not yet set      */
+#define RVL_ENOMEM (-5)
+
+typedef struct rvl_handle rvl_t;
+
+/* A model quantity is either a column of theta (slot >= 0) or a constant
+ * (slot == -1, value used).  Mirrors `pardict = free U fixed`
+ * (evidence/rvmodel/__init__.py:173-178). */
+typedef struct {
+    int32_t slot;
+    int32_t reserved;
+    double value;
+} rvl_param;
+
+/* eccentricity parametrisation, branch order of modelk (:425-447) */
+#define RVL_ECC_DIRECT 0      /* e1 = ecc,   e2 = omega (no validity check) */
+#define RVL_ECC_SECOS_SESIN 1 /* e1 = secos, e2 = sesin; e = c^2+s^2        */
+#define RVL_ECC_ECOS_ESIN 2   /* e1 = ecos,  e2 = esin;  e = sqrt(c^2+s^2)  */
+/* phase parametrisation (:449-454) */
+#define RVL_PHASE_MA0 0 /* phase = ma0                */
+#define RVL_PHASE_ML0 1 /* phase = ml0; M0 = ml0 - omega */
+
+typedef struct {
+    rvl_param amp;    /* k1, or logk1 when amp_is_log       (:412-415) */
+    rvl_param period; /* period, or logperiod when period_is_log (:417-420) */
+    rvl_param e1;
+    rvl_param e2;
+    rvl_param phase;
+    rvl_param epoch; /* planet{n}_epoch (:456) */
+    int32_t amp_is_log;
+    int32_t period_is_log;
+    int32_t ecc_mode;
+    int32_t phase_mode;
+} rvl_planet_desc;
+
+typedef struct {
+    int32_t abi_version; /* RVL_ABI_VERSION */
+    int32_t ndim;        /* number of free parameters = columns of theta */
+    int32_t n_planets;   /* free names containing 'k1'     (:122-124) */
+    int32_t n_inst;
+    int32_t jitter_in_model; /* some free name contains 'jitter' (:138-139) */
+    int32_t drift_in_model;  /* some free name contains 'drift'  (:128-129) */
+    int32_t n_linpar;        /* linear-parameter columns         (:210-212) */
+    int32_t itmax;           /* Newton cap, reference 10000      (:491)     */
+    double tol;              /* Newton |dE| tolerance, reference 1e-4 (:466) */
+    double tref;             /* drift reference time: drift_tref or time[0] (:256-260) */
+    rvl_planet_desc planet[RVL_MAX_PLANETS];
+    rvl_param offset[RVL_MAX_INST]; /* {inst}_offset (:187) */
+    rvl_param jitter[RVL_MAX_INST]; /* {inst}_jitter (:190); ignored unless jitter_in_model */
+    rvl_param drift[4];             /* lin, quad, cub, quar (:246-253) */
+    rvl_param linpar[RVL_MAX_LINPAR];
+} rvl_model_desc;
+
+/* prior kinds: ppf(q), evidence/priors.py */
+#define RVL_PRIOR_UNIFORM 0     /* p0=xmin p1=xmax : xmin + (xmax-xmin) q          (:41-42)  */
+#define RVL_PRIOR_JEFFREYS 1    /* p0=xmin p1=xmax : xmin (xmax/xmin)^q            (:62-63)  */
+#define RVL_PRIOR_MODJEFFREYS 2 /* p0=x0   p1=xmax : x0 (1+xmax/x0)^q - x0         (:82-83)  */
+#define RVL_PRIOR_UNIFORMFREQ 3 /* p0=xmin p1=xmax : xmin / (1 - q (xmax-xmin)/xmax) (:100-101) */
+#define RVL_PRIOR_TRUNCRAYLEIGH 4 /* p0=sigma p1=xmax                              (:249-252) */
+#define RVL_PRIOR_NORMAL 5      /* p0=loc p1=scale : loc + scale ndtri(q)  (stats.norm, :436) */
+#define RVL_PRIOR_LOGNORMAL 6   /* p0=s p1=loc p2=scale : loc + scale exp(s ndtri(q)) (:437)  */
+#define RVL_PRIOR_TABLE 7       /* piecewise-linear inverse CDF through (cdf_k, x_k) knots
+                                   (p0 = 1: result is 10**interp, Log10Normal :144),
+                                   the scheme of the interp1d priors (:118-124,195-202,223-228,
+                                   282-287,321-326,349-354); also used for Beta/Gamma/Alpha */
+
+typedef struct {
+    int32_t kind;
+    int32_t table_len;    /* RVL_PRIOR_TABLE: number of knots */
+    int64_t table_offset; /* RVL_PRIOR_TABLE: offset (in doubles) of the knots inside `tables`:
+                             cdf[0..len) followed by x[0..len) */
+    double p[4];
+} rvl_prior_desc;
+
+typedef struct {
+    uint64_t n_points;       /* lnL evaluations since reset                        */
+    uint64_t n_solves;       /* Kepler solves (point x planet x epoch)             */
+    uint64_t n_newton_iters; /* total Newton iterations actually taken             */
+    uint64_t n_cap_hits;     /* solves that stopped at itmax (reference: :490 ignores -1) */
+    uint64_t n_invalid;      /* points returned as -1e30                           */
+} rvl_counters_t;
+
+/* ---- lifecycle -------------------------------------------------------- */
+int rvl_abi_version(void);
+/* device < 0: use the current CUDA device */
+int rvl_create(rvl_t **out, int device);
+void rvl_destroy(rvl_t *h);
+/* h may be NULL: returns the last error of the calling thread (rvl_create failures) */
+const char *rvl_last_error(const rvl_t *h);
+
+/* ---- staging (once per run) ------------------------------------------- */
+/* Epoch data in the order BaseModel concatenates it (evidence/rvmodel/__init__.py:50-55,
+ * 141-146): time (rjd|jdb), vrad, svrad, inst_id in [0, n_inst). */
+int rvl_set_data(rvl_t *h, const double *t, const double *rv, const double *err,
+                 const int32_t *inst, int32_t n, int32_t n_inst);
+/* linpar_dict[name] column (evidence/rvmodel/__init__.py:210-212) */
+int rvl_set_linpar(rvl_t *h, int32_t idx, const double *col, int32_t n);
+int rvl_set_model(rvl_t *h, const rvl_model_desc *desc);
+int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const double *tables,
+                   int64_t n_table_doubles);
+/* tuning knobs, by name ("variant", "slices", "warps", ...); unknown name -> RVL_EINVAL */
+int rvl_set_option(rvl_t *h, const char *name, int64_t value);
+
+/* ---- hot path: host buffers, synchronous -------------------------------- */
+/* replaces the prior(hypercube) closure, one row per point */
+int rvl_transform(rvl_t *h, const double *U, int64_t B, double *Theta);
+/* replaces the loglike(x) closure / RVModel.log_likelihood, one row per point */
+int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL);
+/* fused u -> theta -> lnL; Theta may be NULL when the sampler does not need it */
+int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, double *lnL);
+
+/* ---- hot path: device buffers, asynchronous on `stream` ------------------ */
+int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream);
+int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, void *stream);
+int rvl_transform_loglike_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta,
+                              double *dlnL, void *stream);
+
+/* ---- the reference's own native FFI, on the device (trueanomaly.h:4) ----- */
+/* Same contract as the reference symbol except: returns -1 when ANY element hit the cap
+ * (every nu[i] is still written from the last iterate, the reference leaves the rest 0). */
+int rvl_trueanomaly(rvl_t *h, const double *M, int32_t n, double ecc, double *nu,
+                    int32_t niterationmax, double tol);
+
+/* ---- observability / measurement ---------------------------------------- */
+int rvl_counters(rvl_t *h, rvl_counters_t *out);
+int rvl_reset_counters(rvl_t *h);
+/* duration (ms, CUDA events on the launching stream) of the last likelihood launch of a
+ * host-buffer call, kernel only */
+int rvl_last_kernel_ms(rvl_t *h, double *ms);
+/* number of kernel launches issued by this handle so far */
+int rvl_launch_count(rvl_t *h, uint64_t *n);
+/* register-resident DFMA loop: measured FP64 peak of this device, TFLOP/s (2 flop per DFMA) */
+int rvl_fp64_peak(rvl_t *h, double *tflops);
+/* sm count, smem per block opt-in, clock (kHz) */
+int rvl_device_info(rvl_t *h, int32_t *sm_count, int32_t *smem_optin, int32_t *clock_khz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVLNL_H */
