@@ -116,38 +116,74 @@ RVL_HD double rcp(double x)
     return y;
 }
 
+// ---- constant table -----------------------------------------------------------------------
+// On the device the coefficients live in the constant bank: FP64 instructions read them as
+// uniform-register / constant operands (LDCU.128 brings two per instruction), instead of the
+// two 32-bit immediate moves per coefficient that literals cost.  Same values on the host.
+#define RVL_K_TABLE                                                                              \
+    {                                                                                            \
+        0x1.45f306dc9c883p-1,          /*  0  2/pi                    */                         \
+        6755399441055744.0,            /*  1  1.5*2^52 (rint trick)   */                         \
+        0x1.921fb54442d18p+0,          /*  2  pi/2 high               */                         \
+        0x1.1a62633145c07p-54,         /*  3  pi/2 middle             */                         \
+        1.58969099521155010221e-10,    /*  4  S6                      */                         \
+        -2.50507602534068634195e-08,   /*  5  S5                      */                         \
+        2.75573137070700676789e-06,    /*  6  S4                      */                         \
+        -1.98412698298579493134e-04,   /*  7  S3                      */                         \
+        8.33333333332248946124e-03,    /*  8  S2                      */                         \
+        -1.66666666666666324348e-01,   /*  9  S1                      */                         \
+        -1.13596475577881948265e-11,   /* 10  C6                      */                         \
+        2.08757232129817482790e-09,    /* 11  C5                      */                         \
+        -2.75573143513906633035e-07,   /* 12  C4                      */                         \
+        2.48015872894767294178e-05,    /* 13  C3                      */                         \
+        -1.38888888888741095749e-03,   /* 14  C2                      */                         \
+        4.16666666666666019037e-02,    /* 15  C1                      */                         \
+        -1.0 / 6.0,                    /* 16                          */                         \
+        -1.0 / 24.0,                   /* 17                          */                         \
+        -1.0 / 5040.0,                 /* 18                          */                         \
+        1.0 / 120.0,                   /* 19                          */                         \
+        1.0 / 40320.0,                 /* 20                          */                         \
+        -1.0 / 720.0,                  /* 21                          */                         \
+        1.0 / 24.0,                    /* 22                          */                         \
+        0.0                            /* 23  (pad)                   */                         \
+    }
+static const double h_ktab[24] = RVL_K_TABLE;
+#if defined(__CUDACC__)
+__constant__ double d_ktab[24] = RVL_K_TABLE;
+#endif
+#if defined(__CUDA_ARCH__)
+#define RVL_K(i) (::rvl::d_ktab[i])
+#else
+#define RVL_K(i) (::rvl::h_ktab[i])
+#endif
+
 // ---- sin & cos of an un-reduced angle ----------------------------------------------------
-// Cody-Waite reduction by pi/2 in three FMA steps (exact for |x| < ~1e5, like CUDA's own fast
-// path), then the classic degree-13/14 minimax kernels on [-pi/4, pi/4] (fdlibm coefficients).
-// 20 FP64 instructions; ~1 ulp.  Callers route |x| >= kTrigFastMax elsewhere.
+// Cody-Waite reduction by pi/2 in two FMA steps (pi/2 to 106 bits: the neglected third term
+// is < 1e-28 for |x| < 1e5), then the classic degree-13/14 minimax kernels on [-pi/4, pi/4]
+// (fdlibm coefficients).  19 FP64 instructions; ~1 ulp.  Callers route |x| >= kTrigFastMax
+// elsewhere (the first reduction step is exact only while |x| 2/pi < 2^17).
 constexpr double kTrigFastMax = 100000.0;
-constexpr double kTwoOverPi = 0x1.45f306dc9c883p-1;
-constexpr double kPio2Hi = 0x1.921fb54442d18p+0;
-constexpr double kPio2Mid = 0x1.1a62633145c07p-54;
-constexpr double kPio2Lo = -0x1.f1976b7ed8fbcp-110;
-constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
 
 RVL_HD void sincos_fast(double x, double &s, double &c)
 {
-    const double q = fma_(x, kTwoOverPi, kMagic);
+    const double q = fma_(x, RVL_K(0), RVL_K(1));
     const int32_t n = lo32(q);
-    const double qf = sub(q, kMagic);
-    double r = fma_(-qf, kPio2Hi, x);
-    r = fma_(-qf, kPio2Mid, r);
-    r = fma_(-qf, kPio2Lo, r);
+    const double qf = sub(q, RVL_K(1));
+    double r = fma_(-qf, RVL_K(2), x);
+    r = fma_(-qf, RVL_K(3), r);
     const double z = mul(r, r);
-    double ps = 1.58969099521155010221e-10;
-    ps = fma_(ps, z, -2.50507602534068634195e-08);
-    ps = fma_(ps, z, 2.75573137070700676789e-06);
-    ps = fma_(ps, z, -1.98412698298579493134e-04);
-    ps = fma_(ps, z, 8.33333333332248946124e-03);
-    ps = fma_(ps, z, -1.66666666666666324348e-01);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma_(pc, z, 2.08757232129817482790e-09);
-    pc = fma_(pc, z, -2.75573143513906633035e-07);
-    pc = fma_(pc, z, 2.48015872894767294178e-05);
-    pc = fma_(pc, z, -1.38888888888741095749e-03);
-    pc = fma_(pc, z, 4.16666666666666019037e-02);
+    double ps = RVL_K(4);
+    ps = fma_(ps, z, RVL_K(5));
+    ps = fma_(ps, z, RVL_K(6));
+    ps = fma_(ps, z, RVL_K(7));
+    ps = fma_(ps, z, RVL_K(8));
+    ps = fma_(ps, z, RVL_K(9));
+    double pc = RVL_K(10);
+    pc = fma_(pc, z, RVL_K(11));
+    pc = fma_(pc, z, RVL_K(12));
+    pc = fma_(pc, z, RVL_K(13));
+    pc = fma_(pc, z, RVL_K(14));
+    pc = fma_(pc, z, RVL_K(15));
     const double sr = fma_(mul(r, z), ps, r);
     const double cr = fma_(z, fma_(z, pc, -0.5), 1.0);
     // quadrant: n mod 4 = 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s)   [integer pipe only]
@@ -168,8 +204,8 @@ RVL_HD void sincos_fast(double x, double &s, double &c)
 RVL_HD void advance_tiny(double d, double &s, double &c)
 {
     const double d2 = mul(d, d);
-    const double sd = fma_(mul(d, d2), -1.0 / 6.0, d);
-    const double v = mul(d2, fma_(d2, -1.0 / 24.0, 0.5));
+    const double sd = fma_(mul(d, d2), RVL_K(16), d);
+    const double v = mul(d2, fma_(d2, RVL_K(17), 0.5));
     const double ds = fma_(c, sd, -mul(s, v));
     const double dc = fma_(s, sd, mul(c, v));
     s = add(s, ds);
@@ -179,13 +215,13 @@ RVL_HD void advance_tiny(double d, double &s, double &c)
 RVL_HD void advance_small(double d, double &s, double &c)
 {
     const double d2 = mul(d, d);
-    double ps = -1.0 / 5040.0;
-    ps = fma_(ps, d2, 1.0 / 120.0);
-    ps = fma_(ps, d2, -1.0 / 6.0);
+    double ps = RVL_K(18);
+    ps = fma_(ps, d2, RVL_K(19));
+    ps = fma_(ps, d2, RVL_K(16));
     const double sd = fma_(mul(d, d2), ps, d);
-    double pc = 1.0 / 40320.0;
-    pc = fma_(pc, d2, -1.0 / 720.0);
-    pc = fma_(pc, d2, 1.0 / 24.0);
+    double pc = RVL_K(20);
+    pc = fma_(pc, d2, RVL_K(21));
+    pc = fma_(pc, d2, RVL_K(22));
     pc = fma_(pc, d2, -0.5);
     const double v = -mul(d2, pc);
     const double ds = fma_(c, sd, -mul(s, v));

@@ -105,72 +105,132 @@ __device__ __forceinline__ double par_of(const rvl_param &p, const double *row)
     return p.slot >= 0 ? __ldg(row + p.slot) : p.value;
 }
 
-__device__ __noinline__ void sincos_slow(double x, double &s, double &c)
+// shared-memory loads through a 32-bit shared-window address (one live register per base
+// pointer; stops the compiler from re-deriving generic addresses inside the hot loops)
+__device__ __forceinline__ double lds_f64(uint32_t addr)
 {
-    sincos(x, &s, &c);  // CUDA libdevice: Payne-Hanek for huge arguments, NaN for inf/nan
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
 }
-__device__ __forceinline__ void sincos_any(double x, double &s, double &c)
+__device__ __forceinline__ int lds_u8(uint32_t addr)
 {
-    if (fabs(x) < rvl::kTrigFastMax)
-        rvl::sincos_fast(x, s, c);
-    else
-        sincos_slow(x, s, c);
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return (int)v;
 }
 
-// ---- one planet, one epoch per lane: Kepler solve + RV term -------------------------------
+// huge / non-finite arguments: CUDA libdevice (Payne-Hanek), out of line and returned by value
+__device__ __noinline__ double2 sincos_slow(double x)
+{
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
+// high word of |x| as an integer: orders like |x| itself (positive doubles sort as integers)
+__device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7fffffff; }
+constexpr int kHiTrigMax = 0x40F86A00;  // 1e5 = 0x40F86A0000000000: |x| < 1e5  <=>  abs_hi < this
+constexpr int kHiTiny = 0x3F500000;     // abs_hi(d) <  this  <=>  |d| <  2^-10
+constexpr int kHiSmall = 0x3FA00000;    // abs_hi(d) <  this  <=>  |d| <  2^-5
+
+// ---- U epochs per lane x one planet: Kepler solves + RV terms -------------------------------
 // VARIANT 0: optimised (reciprocal-multiply Newton step, warp-uniform small-step sin/cos
 //            advance).  VARIANT 1: conservative (IEEE division, full sin/cos every step) — kept
 //            as the in-product cross-check of the optimisations, selectable with
 //            rvl_set_option("variant", 1).
-template <int VARIANT>
-__device__ __forceinline__ double solve_planet(double t, const double *pc, double tol, int itmax,
-                                               int &iters, int &caps)
+// U independent solves per lane (instruction-level parallelism; control flow, votes and constant
+// loads are shared by the U solves).
+// Lanes freeze individually (trueanomaly.c:21: per-element stop): a frozen lane's step is forced
+// to 0, so its E never moves again and `|d| > tol` keeps it inactive without a separate flag.
+template <int VARIANT, int U>
+__device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, double tol,
+                                             int itmax, double (&rv)[U], int (&iters)[U],
+                                             int &caps)
 {
-    const double nmot = pc[0], M0 = pc[1], ec = pc[2], A = pc[3], Bs = pc[4], Ce = pc[5],
-                 epoch = pc[6];
-    const double M = rvl::mean_anomaly(nmot, t, epoch, M0);
-    double E = M, s, c;
-    sincos_any(E, s, c);
-    bool active = true;
-    int it = 0;
-    while (true) {
-        double d = 0.0;
-        if (active) {
+    const double nmot = lds_f64(pc), M0 = lds_f64(pc + 8), ec = lds_f64(pc + 16),
+                 epoch = lds_f64(pc + 48);
+    double M[U], E[U], s[U], c[U], d[U];
+    int last[U];
+    bool big = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        M[u] = rvl::mean_anomaly(nmot, t[u], epoch, M0);
+        E[u] = M[u];
+        big = big || !(abs_hi(M[u]) < kHiTrigMax);
+        d[u] = 1e300;  // "not yet converged"
+        last[u] = 0;
+    }
+    // slow: some |M| >= 1e5 (or non-finite), or an eccentricity outside [-0.99, 0.99] (only
+    // reachable with a nonsensical direct `ecc`): every sin/cos of this solve goes through
+    // libdevice, which is valid for any argument
+    const bool slow = __any_sync(kFull, big || !(ec >= -0.99));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (slow) {
+            const double2 r = sincos_slow(E[u]);
+            s[u] = r.x;
+            c[u] = r.y;
+        } else {
+            rvl::sincos_fast(E[u], s[u], c[u]);
+        }
+    }
+    int trip = 0;  // warp-uniform
+    bool any_left;
+    for (;;) {
+        bool pa[U];
+        any_left = false;
+        const bool room = trip < itmax;  // trueanomaly.c:32-33 (lanes still active hit the cap)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pa[u] = (fabs(d[u]) > tol) && room;  // trueanomaly.c:21
+            any_left = any_left || pa[u];
+        }
+        if (!__any_sync(kFull, any_left)) break;
+        ++trip;
+        int hmax = 0, emax = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
             double En;
             if (VARIANT == 0) {
-                d = rvl::newton_step(E, s, c, M, ec, En);
+                rvl::newton_step(E[u], s[u], c[u], M[u], ec, En);
             } else {
-                const double f = rvl::sub(rvl::sub(E, rvl::mul(ec, s)), M);
-                const double fp = rvl::sub(1.0, rvl::mul(ec, c));
-                En = rvl::sub(E, __ddiv_rn(f, fp));
-                d = rvl::sub(En, E);
+                const double f = rvl::sub(rvl::sub(E[u], rvl::mul(ec, s[u])), M[u]);
+                const double fp = rvl::sub(1.0, rvl::mul(ec, c[u]));
+                En = rvl::sub(E[u], __ddiv_rn(f, fp));
             }
-            E = En;
-            ++it;
-            if (it >= itmax) {  // trueanomaly.c:32-33: the cap is tested before convergence
-                active = false;
-                ++caps;
-            } else if (!(fabs(d) > tol)) {  // trueanomaly.c:21
-                active = false;
-            }
+            En = pa[u] ? En : E[u];
+            d[u] = rvl::sub(En, E[u]);  // exact; 0 for frozen lanes
+            E[u] = En;
+            last[u] = pa[u] ? trip : last[u];
+            hmax = max(hmax, abs_hi(d[u]));
+            emax = max(emax, abs_hi(En));
         }
-        const double ad = fabs(d);
-        if (VARIANT == 0 && __all_sync(kFull, ad <= rvl::kTinyStep)) {
-            rvl::advance_tiny(d, s, c);
-        } else if (VARIANT == 0 && __all_sync(kFull, ad <= rvl::kSmallStep)) {
-            rvl::advance_small(d, s, c);
+        if (VARIANT == 0 && __all_sync(kFull, hmax < kHiTiny)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvl::advance_tiny(d[u], s[u], c[u]);
+        } else if (VARIANT == 0 && __all_sync(kFull, hmax < kHiSmall)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvl::advance_small(d[u], s[u], c[u]);
+        } else if (slow || (trip > 2 && __any_sync(kFull, !(emax < kHiTrigMax)))) {
+            // |E| can only leave the fast range after >= 3 Newton steps (|step| <= 100 |f|)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double2 r = sincos_slow(E[u]);
+                s[u] = r.x;
+                c[u] = r.y;
+            }
         } else {
-            double s2, c2;
-            sincos_any(E, s2, c2);
-            if (d != 0.0) {  // lanes that did not move keep their (s, c) bit for bit
-                s = s2;
-                c = c2;
-            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvl::sincos_fast(E[u], s[u], c[u]);
         }
-        if (!__any_sync(kFull, active)) break;
     }
-    iters += it;
-    return rvl::kepler_rv(s, c, ec, A, Bs, Ce);
+    const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        iters[u] += last[u];
+        caps += (fabs(d[u]) > tol) ? 1 : 0;
+        rv[u] = rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce);
+    }
 }
 
 // ---- per-point setup: theta row -> per-warp constants (modelk :411-457, :181-192) ---------
@@ -234,8 +294,10 @@ __device__ __forceinline__ bool point_setup(const rvl_model_desc &m, const doubl
 }
 
 // ---- the likelihood kernel ------------------------------------------------------------------
-template <int VARIANT>
-__global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
+// U = epochs per lane in flight (1: 1024 threads/SM at <=64 registers; 2: 512 threads/SM at
+// <=128 registers, two chunks of 32 epochs per warp trip).
+template <int VARIANT, int U>
+__global__ void __launch_bounds__(U == 1 ? 1024 : 512, 1) rv_lnl_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [0,8) mbarrier | [128, 128+sizeof(model)) model | epoch columns | inst ids | warp consts
@@ -282,13 +344,16 @@ __global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
     const int itmax = m.itmax;
     const bool has_drift = m.drift_in_model != 0;
     const int nlin = m.n_linpar;
-    const double *s_t = scol, *s_rv = scol + ne, *s_s2 = scol + 2 * (size_t)ne;
-    const double *s_tt = scol + 3 * (size_t)ne;  // valid when has_drift
-    const double *s_lin = scol + (size_t)(3 + (has_drift ? 1 : 0)) * ne;
     double *wc = wconst + (size_t)warp * a.wstride;
-    const double *ic = wc + K * kPlanetStride;
-    const double *dc = ic + 2 * m.n_inst;
-    const int e_base = c0 * 32;  // global epoch index of the slice start
+    // 32-bit shared-window addresses of everything the hot loop reads
+    const uint32_t a_wc = smem_u32(wc);
+    const uint32_t a_ic = a_wc + (uint32_t)(K * kPlanetStride) * 8u;
+    const uint32_t a_dc = a_ic + (uint32_t)(2 * m.n_inst) * 8u;
+    const uint32_t a_t = smem_u32(scol) + (uint32_t)lane * 8u;
+    const uint32_t colb = (uint32_t)ne * 8u;  // bytes per column
+    const uint32_t a_inst = smem_u32(sinst) + (uint32_t)lane;
+    const uint32_t lin0 = (uint32_t)(3 + (has_drift ? 1 : 0)) * colb;
+    const int e_base = c0 * 32 + lane;  // global epoch index of this lane in chunk 0
 
     unsigned long long tot_iters = 0, tot_caps = 0, tot_invalid = 0;
 
@@ -307,48 +372,65 @@ __global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
         int esum = 0, iters = 0, caps = 0;
         bool ok = true;
         if (valid) {
-            for (int ch = 0; ch < nch; ++ch) {
-                const int j = ch * 32 + lane;
-                const bool live = (e_base + j) < a.N;
-                const double t = s_t[j];
-                double rvsum = 0.0;
-                int it_l = 0, cap_l = 0;
+            for (int ch = 0; ch < nch; ch += U) {
+                // U chunks of 32 epochs; a missing last chunk repeats the previous one, masked
+                uint32_t off[U];
+                bool live[U];
+                double t[U], rvsum[U];
+                int it_l[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool have = (ch + u) < nch;
+                    const int cu = have ? ch + u : ch;
+                    off[u] = (uint32_t)cu * 256u;
+                    live[u] = have && (e_base + cu * 32) < a.N;
+                    t[u] = lds_f64(a_t + off[u]);
+                    rvsum[u] = 0.0;
+                    it_l[u] = 0;
+                }
+                int cap_l = 0;
                 for (int p = 0; p < K; ++p) {
-                    const double v = solve_planet<VARIANT>(t, wc + p * kPlanetStride, tol, itmax,
-                                                           it_l, cap_l);
-                    rvsum = (p == 0) ? v : rvl::add(rvsum, v);
+                    double v[U];
+                    solve_planet<VARIANT, U>(t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
+                                             itmax, v, it_l, cap_l);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) rvsum[u] = (p == 0) ? v[u] : rvl::add(rvsum[u], v[u]);
                 }
-                if (live) {  // padded lanes of the last chunk re-solve the last epoch: not counted
-                    iters += it_l;
-                    caps += cap_l;
+                caps += cap_l;  // (padded / repeated lanes included: a cap hit is a cap hit)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t ae = a_t + off[u];
+                    const int ii = lds_u8(a_inst + off[u] / 8u);
+                    const uint32_t ai = a_ic + (uint32_t)ii * 16u;
+                    double rvm = lds_f64(ai);
+                    if (K > 0) rvm = rvl::add(rvm, rvsum[u]);
+                    if (has_drift) {
+                        const double tt = lds_f64(ae + 3u * colb);
+                        const double t2 = rvl::mul(tt, tt);
+                        double dr = rvl::mul(lds_f64(a_dc), tt);
+                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 8), t2));
+                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 16), rvl::mul(t2, tt)));
+                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 24), rvl::mul(t2, t2)));
+                        rvm = rvl::add(rvm, dr);
+                    }
+                    for (int l = 0; l < nlin; ++l)
+                        rvm = rvl::add(rvm, rvl::mul(lds_f64(a_dc + 32u + (uint32_t)l * 8u),
+                                                     lds_f64(ae + lin0 + (uint32_t)l * colb)));
+                    const double res = rvl::sub(lds_f64(ae + colb), rvm);
+                    const double var = rvl::add(lds_f64(ae + 2u * colb), lds_f64(ai + 8));
+                    const double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
+                    double mant;
+                    int ex;
+                    const bool okv = rvl::split_pos(var, mant, ex);
+                    if (live[u]) {
+                        chi = rvl::add(chi, term);
+                        prod = rvl::mul(prod, mant);
+                        esum += ex;
+                        ok = ok && okv;
+                        iters += it_l[u];
+                    }
                 }
-                const int ii = sinst[j];
-                double rvm = ic[2 * ii];
-                if (K > 0) rvm = rvl::add(rvm, rvsum);
-                if (has_drift) {
-                    const double tt = s_tt[j];
-                    const double t2 = rvl::mul(tt, tt);
-                    double dr = rvl::mul(dc[0], tt);
-                    dr = rvl::add(dr, rvl::mul(dc[1], t2));
-                    dr = rvl::add(dr, rvl::mul(dc[2], rvl::mul(t2, tt)));
-                    dr = rvl::add(dr, rvl::mul(dc[3], rvl::mul(t2, t2)));
-                    rvm = rvl::add(rvm, dr);
-                }
-                for (int l = 0; l < nlin; ++l)
-                    rvm = rvl::add(rvm, rvl::mul(dc[4 + l], s_lin[(size_t)l * ne + j]));
-                const double res = rvl::sub(s_rv[j], rvm);
-                const double var = rvl::add(s_s2[j], ic[2 * ii + 1]);
-                double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
-                double mant;
-                int ex;
-                const bool okv = rvl::split_pos(var, mant, ex);
-                if (live) {
-                    chi = rvl::add(chi, term);
-                    prod = rvl::mul(prod, mant);
-                    esum += ex;
-                    ok = ok && okv;
-                }
-                if ((ch & 511) == 511) {  // keep the mantissa product inside the double range
+                if ((ch & 255) == 254 || (ch & 255) == 255) {  // keep the mantissa product in range
                     double mm;
                     int ee;
                     rvl::split_pos(prod, mm, ee);
@@ -357,6 +439,7 @@ __global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
                 }
             }
         }
+
         // ---- slice reduction: chi^2 sum, mantissa product, exponent sum ----
         double S1, S2;
         if (valid) {
@@ -365,7 +448,7 @@ __global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     chi = rvl::add(chi, __shfl_xor_sync(kFull, chi, o));
-                    if (o == 4) {  // 8 lanes x <=512 mantissas each can reach 2^1023: renormalise
+                    {  // renormalise the mantissa product to [1,2) before every pairing
                         double mm;
                         int ee;
                         rvl::split_pos(prod, mm, ee);
@@ -383,9 +466,11 @@ __global__ void __launch_bounds__(1024, 1) rv_lnl_kernel(const KArgs a)
                 // a variance that is zero / subnormal / negative / non-finite: plain logs
                 double acc = 0.0;
                 for (int ch = 0; ch < nch; ++ch) {
-                    const int j = ch * 32 + lane;
-                    if ((e_base + j) < a.N) {
-                        const double var = rvl::add(s_s2[j], ic[2 * (int)sinst[j] + 1]);
+                    const uint32_t o8 = (uint32_t)ch * 256u;
+                    if ((e_base + ch * 32) < a.N) {
+                        const int ii = lds_u8(a_inst + o8 / 8u);
+                        const double var = rvl::add(lds_f64(a_t + o8 + 2u * colb),
+                                                    lds_f64(a_ic + (uint32_t)ii * 16u + 8u));
                         acc = rvl::add(acc, log(sqrt(var)));
                     }
                 }
@@ -501,6 +586,10 @@ __global__ void prior_transform_kernel(const rvl_prior_desc *priors, const doubl
 }
 
 // ---- the reference's native FFI on the device (trueanomaly.h:4) --------------------------------
+// One warp per 32 elements; a per-warp constant block in shared memory feeds solve_planet with
+// nmot = 0, epoch = 0, M0 = M[i]: mean_anomaly gives 0*(t-0) + M[i] = M[i] exactly, and
+// A = 1, Bs = 0, Ce = 0 / A = 0, Bs = 1 turn the RV term into cos(nu) / -sin(nu)... simpler and
+// exact: replay the same loop on (sin E, cos E) and finish with atan2.
 __global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *nu, int itmax,
                                    double tol, int *caphit)
 {
@@ -508,30 +597,28 @@ __global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *n
     const int ii = min(i, n - 1);  // whole warps stay converged; extra lanes duplicate the last
     const double ec = ecc > 0.99 ? 0.99 : ecc;
     const double m = __ldg(M + ii);
-    double E = m, s, c;
-    sincos_any(E, s, c);
-    bool active = true;
-    int it = 0, cap = 0;
-    while (true) {
-        double d = 0.0;
-        if (active) {
-            double En;
-            d = rvl::newton_step(E, s, c, m, ec, En);
-            E = En;
-            ++it;
-            if (it >= itmax) { active = false; cap = 1; }
-            else if (!(fabs(d) > tol)) active = false;
-        }
-        const double ad = fabs(d);
-        if (__all_sync(kFull, ad <= rvl::kTinyStep)) rvl::advance_tiny(d, s, c);
-        else if (__all_sync(kFull, ad <= rvl::kSmallStep)) rvl::advance_small(d, s, c);
-        else {
-            double s2, c2;
-            sincos_any(E, s2, c2);
-            if (d != 0.0) { s = s2; c = c2; }
-        }
-        if (!__any_sync(kFull, active)) break;
+    double E = m, s, c, d = 1e300;
+    const bool slow = __any_sync(kFull, !(abs_hi(m) < kHiTrigMax) || !(ec >= -0.99));
+    if (slow) { const double2 r = sincos_slow(E); s = r.x; c = r.y; }
+    else rvl::sincos_fast(E, s, c);
+    int trip = 0;
+    for (;;) {
+        const bool pa = (fabs(d) > tol) && trip < itmax;
+        if (!__any_sync(kFull, pa)) break;
+        ++trip;
+        double En;
+        rvl::newton_step(E, s, c, m, ec, En);
+        En = pa ? En : E;
+        d = rvl::sub(En, E);
+        E = En;
+        const int h = abs_hi(d);
+        if (__all_sync(kFull, h < kHiTiny)) rvl::advance_tiny(d, s, c);
+        else if (__all_sync(kFull, h < kHiSmall)) rvl::advance_small(d, s, c);
+        else if (slow || (trip > 2 && __any_sync(kFull, !(abs_hi(E) < kHiTrigMax)))) {
+            const double2 r = sincos_slow(E); s = r.x; c = r.y;
+        } else rvl::sincos_fast(E, s, c);
     }
+    const int cap = (fabs(d) > tol) ? 1 : 0;
     if (i < n) {
         // nu = 2 atan(sqrt((1+e)/(1-e)) tan(E/2))  ==  atan2(sqrt(1-e^2) sin E, cos E - e)
         const double root = sqrt(rvl::mul(rvl::sub(1.0, ec), rvl::add(1.0, ec)));
@@ -596,7 +683,7 @@ struct rvl_handle {
     unsigned int *d_work = nullptr;            // sm_count
 
     // options
-    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1;
+    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1, opt_ilp = 1;
 
     // bookkeeping
     uint64_t n_points = 0, n_solves = 0, launches = 0;
@@ -690,7 +777,7 @@ int ensure_partial(rvl_t *h, long long B, int S)
 }
 
 struct Plan {
-    int S, cps, W, grid, wstride;
+    int S, cps, W, U, grid, wstride;
     size_t smem;
 };
 
@@ -706,8 +793,9 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     const int Ctot = h->Npad / 32;
     int wstride = m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar;
     wstride = (wstride + 1) & ~1;
-    int W = h->opt_warps > 0 ? h->opt_warps : 32;
-    W = std::max(1, std::min(32, W));
+    const int U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
+    int W = h->opt_warps > 0 ? h->opt_warps : (U == 2 ? 16 : 32);
+    W = std::max(1, std::min(U == 2 ? 16 : 32, W));
     // smallest slice count whose slice fits in shared memory
     int S = 1;
     auto fits = [&](int s) {
@@ -730,18 +818,18 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     int cps = (Ctot + S - 1) / S;
     S = (Ctot + cps - 1) / cps;  // drop empty trailing slices
     if (!fits(S)) return fail(h, RVL_EINVAL, "slice does not fit in shared memory");
-    pl.S = S; pl.cps = cps; pl.W = W; pl.wstride = wstride;
+    pl.S = S; pl.cps = cps; pl.W = W; pl.U = U; pl.wstride = wstride;
     pl.grid = std::max(1, h->sm_count / S) * S;
     pl.smem = smem_need(h->ncol, cps * 32, W, wstride);
     return RVL_OK;
 }
 
-template <int V>
+template <int V, int U>
 int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
 {
-    CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                h->smem_optin));
-    rv_lnl_kernel<V><<<pl.grid, pl.W * 32, pl.smem, st>>>(a);
+    rv_lnl_kernel<V, U><<<pl.grid, pl.W * 32, pl.smem, st>>>(a);
     CU(h, cudaGetLastError());
     return RVL_OK;
 }
@@ -766,7 +854,9 @@ int enqueue_loglike(rvl_t *h, const double *dTheta, long long B, double *dlnL, c
     a.S = pl.S; a.cps = pl.cps; a.wstride = pl.wstride;
     CU(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned) * (size_t)h->sm_count, st));
     if (timed) CU(h, cudaEventRecord(h->ev0, st));
-    rc = h->opt_variant == 1 ? launch_lnl_v<1>(h, a, pl, st) : launch_lnl_v<0>(h, a, pl, st);
+    if (h->opt_variant == 1) rc = launch_lnl_v<1, 1>(h, a, pl, st);
+    else if (pl.U == 2) rc = launch_lnl_v<0, 2>(h, a, pl, st);
+    else rc = launch_lnl_v<0, 1>(h, a, pl, st);
     if (rc) return rc;
     if (timed) { CU(h, cudaEventRecord(h->ev1, st)); h->timing_pending = true; }
     ++h->launches;
@@ -973,6 +1063,7 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
     else if (n == "slices") h->opt_slices = (int)std::max<int64_t>(0, value);
     else if (n == "warps") h->opt_warps = (int)std::max<int64_t>(0, std::min<int64_t>(32, value));
     else if (n == "timing") h->opt_timing = value != 0;
+    else if (n == "ilp") { if (value != 1 && value != 2) return fail(h, RVL_EINVAL, "ilp in {1,2}"); h->opt_ilp = (int)value; }
     else return fail(h, RVL_EINVAL, "unknown option " + n);
     return RVL_OK;
 }

@@ -1,0 +1,166 @@
+"""
+A small, seeded, fully vectorised nested sampler.
+
+The reference delegates sampling to third-party packages (UltraNest, PolyChord) that are not part
+of its repository and are absent from this image.  The runner in
+``evidence_b200.ultranest`` uses UltraNest when it is importable; this module is the stand-in
+that makes end-to-end ln Z runs possible without it, and -- because it is deterministic for a
+given seed -- lets the SAME sampler code be driven by the device likelihood and by the CPU oracle
+to check that the two agree on ln Z (BASELINE.json north_star).
+
+Algorithm: classic nested sampling (Skilling 2006) with rejection sampling from a single
+bounding ellipsoid of the live points in unit-cube space (as MultiNest's ellipsoidal mode with
+one ellipsoid / nestle's 'single' bound), enlarged by ``enlarge`` in radius.  Candidates are
+drawn and evaluated in batches of ``ndraw`` -- the large vectorised batches the device path is
+built for -- and consumed in order; a candidate drawn under an older (larger) bound is still a
+fair draw from the prior restricted to any later likelihood contour, so a batch feeds many
+iterations.  ln Z and its uncertainty follow Skilling's estimate
+sigma = sqrt(H / nlive).
+"""
+import numpy as np
+
+
+class NestedResult(dict):
+    __getattr__ = dict.get
+
+
+def _logaddexp(a, b):
+    return np.logaddexp(a, b)
+
+
+def _bounding_ellipsoid(u, enlarge, wrapped=None):
+    """Centre, Cholesky factor of the enlarged bounding ellipsoid of points u[n, d]."""
+    n, d = u.shape
+    ctr = u.mean(axis=0)
+    delta = u - ctr
+    cov = delta.T @ delta / max(1, n - 1)
+    cov += np.eye(d) * 1e-14 * max(1e-300, np.trace(cov) / d)
+    try:
+        L = np.linalg.cholesky(cov)
+    except np.linalg.LinAlgError:
+        L = np.diag(np.sqrt(np.maximum(np.diag(cov), 1e-30)))
+    y = np.linalg.solve(L, delta.T)
+    rmax = np.sqrt(np.max(np.sum(y * y, axis=0)))
+    return ctr, L * (rmax * enlarge)
+
+
+def _draw_in_ellipsoid(rng, ctr, L, n):
+    d = len(ctr)
+    z = rng.standard_normal((n, d))
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    r = rng.random(n) ** (1.0 / d)
+    return ctr + (z * r[:, None]) @ L.T
+
+
+def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, frac_remain=0.01,
+                  enlarge=1.15, seed=0, max_calls=50_000_000, update_interval=None,
+                  verbose=False):
+    """
+    loglike(theta[n, ndim]) -> lnL[n] and transform(u[n, ndim]) -> theta[n, ndim] are the
+    vectorised callbacks (UltraNest's ``vectorized=True`` convention).
+
+    Stops when the live points' remaining evidence falls below ``frac_remain`` of the total, or
+    their ln Z contribution below ``dlogz`` -- the two UltraNest criteria the reference sets
+    (evidence/ultranest/__init__.py:181-185).
+    """
+    rng = np.random.default_rng(seed)
+    u_live = rng.random((nlive, ndim))
+    th_live = transform(u_live)
+    l_live = np.asarray(loglike(th_live), dtype=np.float64)
+    ncall = nlive
+    update_interval = update_interval or max(1, nlive // 2)
+
+    logz = -np.inf
+    h_info = 0.0
+    logx = 0.0  # ln prior volume
+    dead_theta, dead_logl, dead_logw = [], [], []
+    pool_u = np.zeros((0, ndim))
+    pool_th = np.zeros((0, ndim))
+    pool_l = np.zeros(0)
+    pool_pos = 0
+    since_update = update_interval  # force a bound on first use
+    ctr = L = None
+    it = 0
+    log_shrink = np.log1p(-1.0 / (nlive + 1.0))  # E[ln t] per iteration ~ -1/nlive
+    while True:
+        worst = int(np.argmin(l_live))
+        lstar = l_live[worst]
+        logx_new = logx - 1.0 / nlive
+        logw = np.log(np.exp(logx) - np.exp(logx_new)) if logx > -700 else logx + np.log1p(-np.exp(-1.0 / nlive))
+        contrib = lstar + logw
+        logz_new = _logaddexp(logz, contrib)
+        if np.isfinite(logz_new):
+            h_info = (np.exp(contrib - logz_new) * lstar
+                      + (np.exp(logz - logz_new) * (h_info + logz) if np.isfinite(logz) else 0.0)
+                      - logz_new)
+        logz = logz_new
+        dead_theta.append(th_live[worst].copy())
+        dead_logl.append(lstar)
+        dead_logw.append(logw)
+        logx = logx_new
+        it += 1
+
+        # replacement: next pooled candidate above the new threshold
+        found = False
+        while not found:
+            while pool_pos < len(pool_l):
+                k = pool_pos
+                pool_pos += 1
+                if pool_l[k] > lstar:
+                    u_live[worst], th_live[worst], l_live[worst] = pool_u[k], pool_th[k], pool_l[k]
+                    found = True
+                    break
+            if found:
+                break
+            if since_update >= update_interval or ctr is None:
+                ctr, L = _bounding_ellipsoid(u_live, enlarge)
+                since_update = 0
+            cand = _draw_in_ellipsoid(rng, ctr, L, ndraw)
+            inside = np.all((cand >= 0.0) & (cand < 1.0), axis=1)
+            cand = cand[inside]
+            if len(cand) == 0:
+                continue
+            pool_u = cand
+            pool_th = transform(cand)
+            pool_l = np.asarray(loglike(pool_th), dtype=np.float64)
+            pool_pos = 0
+            ncall += len(cand)
+            if ncall > max_calls:
+                raise RuntimeError("nested_sample: max_calls exceeded")
+        since_update += 1
+
+        # termination on the live points' remaining evidence
+        lmax = np.max(l_live)
+        log_remain = lmax + logx
+        if it % 50 == 0 or True:
+            if log_remain - _logaddexp(logz, log_remain) < np.log(frac_remain) or \
+                    _logaddexp(logz, log_remain) - logz < dlogz * 1e-3:
+                break
+        if verbose and it % 500 == 0:
+            print(f"it={it} lnZ={logz:.3f} remain={log_remain - logz:.2f} ncall={ncall}")
+
+    # final live-point contribution
+    logw_live = logx - np.log(nlive)
+    for k in np.argsort(l_live):
+        contrib = l_live[k] + logw_live
+        logz_new = _logaddexp(logz, contrib)
+        h_info = (np.exp(contrib - logz_new) * l_live[k]
+                  + np.exp(logz - logz_new) * (h_info + logz) - logz_new)
+        logz = logz_new
+        dead_theta.append(th_live[k].copy())
+        dead_logl.append(l_live[k])
+        dead_logw.append(logw_live)
+    dead_logl = np.array(dead_logl)
+    dead_logw = np.array(dead_logw)
+    logwt = dead_logl + dead_logw - logz
+    weights = np.exp(logwt - np.max(logwt))
+    weights /= weights.sum()
+    theta = np.array(dead_theta)
+    # equally weighted posterior samples (systematic resampling, seeded)
+    nsamp = max(1, int(1.0 / np.sum(weights ** 2)))
+    pos = (rng.random() + np.arange(nsamp)) / nsamp
+    idx = np.minimum(np.searchsorted(np.cumsum(weights), pos), len(weights) - 1)
+    return NestedResult(logz=float(logz), logzerr=float(np.sqrt(max(h_info, 0.0) / nlive)),
+                        ncall=int(ncall), niter=int(it), information=float(h_info),
+                        samples=theta[idx], weighted_samples=theta, weights=weights,
+                        logl=dead_logl, nlive=nlive, seed=seed)

@@ -29,61 +29,76 @@ struct Stats {
 
 inline double par_of(const rvl_param &p, const double *row) { return p.slot >= 0 ? row[p.slot] : p.value; }
 
-inline void sincos_any(double x, double &s, double &c)
-{
-    if (fabs(x) < rvl::kTrigFastMax) rvl::sincos_fast(x, s, c);
-    else { s = sin(x); c = cos(x); }
-}
 
-// one planet for the 32 epochs of a chunk, in lock-step (mirrors solve_planet<0>)
-void solve_planet_warp(const double *t, const double *pc, double tol, int itmax, double *out,
-                       int *iters, int *caps, Stats &st)
+inline int abs_hi(double x) { return rvl::hi32(x) & 0x7fffffff; }
+constexpr int kHiTrigMax = 0x40F86A00, kHiTiny = 0x3F500000, kHiSmall = 0x3FA00000;
+
+// one planet for U chunks of 32 epochs (U*32 solves) in lock-step: mirrors solve_planet<0, U>
+void solve_planet_warp(int U, const double *const *t, const double *pc, double tol, int itmax,
+                       double (*out)[W], int (*iters)[W], int *caps, Stats &st)
 {
     const double nmot = pc[0], M0 = pc[1], ec = pc[2], A = pc[3], Bs = pc[4], Ce = pc[5], epoch = pc[6];
-    double M[W], E[W], s[W], c[W], d[W];
-    bool active[W];
-    int it[W];
-    for (int l = 0; l < W; ++l) {
-        M[l] = rvl::mean_anomaly(nmot, t[l], epoch, M0);
-        E[l] = M[l];
-        sincos_any(E[l], s[l], c[l]);
-        active[l] = true;
-        it[l] = 0;
-    }
-    ++st.solves_warp;
-    while (true) {
-        bool all_tiny = true, all_small = true, any_active = false;
+    double M[2][W], E[2][W], s[2][W], c[2][W], d[2][W];
+    int last[2][W];
+    bool big = false;
+    for (int u = 0; u < U; ++u)
         for (int l = 0; l < W; ++l) {
-            d[l] = 0.0;
-            if (active[l]) {
-                double En;
-                d[l] = rvl::newton_step(E[l], s[l], c[l], M[l], ec, En);
-                E[l] = En;
-                ++it[l];
-                if (it[l] >= itmax) { active[l] = false; ++caps[l]; }
-                else if (!(fabs(d[l]) > tol)) active[l] = false;
-            }
-            const double ad = fabs(d[l]);
-            all_tiny = all_tiny && (ad <= rvl::kTinyStep);
-            all_small = all_small && (ad <= rvl::kSmallStep);
-            any_active = any_active || active[l];
+            M[u][l] = rvl::mean_anomaly(nmot, t[u][l], epoch, M0);
+            E[u][l] = M[u][l];
+            big = big || !(abs_hi(M[u][l]) < kHiTrigMax);
+            d[u][l] = 1e300;
+            last[u][l] = 0;
         }
-        if (all_tiny) { ++st.trips_tiny; for (int l = 0; l < W; ++l) rvl::advance_tiny(d[l], s[l], c[l]); }
-        else if (all_small) { ++st.trips_small; for (int l = 0; l < W; ++l) rvl::advance_small(d[l], s[l], c[l]); }
+    const bool slow = big || !(ec >= -0.99);
+    for (int u = 0; u < U; ++u)
+        for (int l = 0; l < W; ++l) {
+            if (slow) { s[u][l] = sin(E[u][l]); c[u][l] = cos(E[u][l]); }
+            else rvl::sincos_fast(E[u][l], s[u][l], c[u][l]);
+        }
+    ++st.solves_warp;
+    int trip = 0;
+    for (;;) {
+        bool pa[2][W], any_left = false;
+        const bool room = trip < itmax;
+        for (int u = 0; u < U; ++u)
+            for (int l = 0; l < W; ++l) {
+                pa[u][l] = (fabs(d[u][l]) > tol) && room;
+                any_left = any_left || pa[u][l];
+            }
+        if (!any_left) break;
+        ++trip;
+        bool all_tiny = true, all_small = true, any_big = false;
+        for (int u = 0; u < U; ++u)
+            for (int l = 0; l < W; ++l) {
+                double En;
+                rvl::newton_step(E[u][l], s[u][l], c[u][l], M[u][l], ec, En);
+                En = pa[u][l] ? En : E[u][l];
+                d[u][l] = En - E[u][l];
+                E[u][l] = En;
+                last[u][l] = pa[u][l] ? trip : last[u][l];
+                const int h = abs_hi(d[u][l]);
+                all_tiny = all_tiny && (h < kHiTiny);
+                all_small = all_small && (h < kHiSmall);
+                any_big = any_big || !(abs_hi(En) < kHiTrigMax);
+            }
+        if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(d[u][l], s[u][l], c[u][l]); }
+        else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(d[u][l], s[u][l], c[u][l]); }
         else {
             ++st.trips_full;
-            for (int l = 0; l < W; ++l) {
-                double s2, c2;
-                sincos_any(E[l], s2, c2);
-                if (d[l] != 0.0) { s[l] = s2; c[l] = c2; }
-            }
+            const bool lib = slow || (trip > 2 && any_big);
+            for (int u = 0; u < U; ++u)
+                for (int l = 0; l < W; ++l) {
+                    if (lib) { s[u][l] = sin(E[u][l]); c[u][l] = cos(E[u][l]); }
+                    else rvl::sincos_fast(E[u][l], s[u][l], c[u][l]);
+                }
         }
-        if (!any_active) break;
     }
-    for (int l = 0; l < W; ++l) {
-        iters[l] += it[l];
-        out[l] = rvl::kepler_rv(s[l], c[l], ec, A, Bs, Ce);
-    }
+    for (int u = 0; u < U; ++u)
+        for (int l = 0; l < W; ++l) {
+            iters[u][l] += last[u][l];
+            caps[l] += (fabs(d[u][l]) > tol) ? 1 : 0;
+            out[u][l] = rvl::kepler_rv(s[u][l], c[u][l], ec, A, Bs, Ce);
+        }
 }
 
 bool point_setup(const rvl_model_desc &m, const double *row, double *wc)
@@ -129,8 +144,9 @@ bool point_setup(const rvl_model_desc &m, const double *row, double *wc)
 extern "C" int emul_loglike(const rvl_model_desc *mp, const double *t, const double *rv,
                             const double *err, const int32_t *inst, int N,
                             const double *const *linpar, const double *theta, long long B, int S,
-                            double *lnl, long long *stats_out)
+                            int U, double *lnl, long long *stats_out)
 {
+    if (U != 2) U = 1;
     const rvl_model_desc &m = *mp;
     const int Npad = (N + 31) / 32 * 32, Ctot = Npad / 32, K = m.n_planets;
     if (S < 1) S = 1;
@@ -164,40 +180,52 @@ extern "C" int emul_loglike(const rvl_model_desc *mp, const double *t, const dou
             int esum[W], iters[W], caps[W];
             bool ok[W];
             for (int l = 0; l < W; ++l) { chi[l] = 0; prod[l] = 1; esum[l] = 0; iters[l] = 0; caps[l] = 0; ok[l] = true; }
-            for (int ch = 0; ch < nch; ++ch) {
-                const int j0 = (c0 + ch) * 32;
-                double rvsum[W], v[W];
-                int it_l[W], cap_l[W];
-                for (int l = 0; l < W; ++l) { rvsum[l] = 0; it_l[l] = 0; cap_l[l] = 0; }
+            for (int ch = 0; ch < nch; ch += U) {
+                int j0[2];
+                bool have[2];
+                const double *tp[2];
+                double rvsum[2][W], v[2][W];
+                int it_l[2][W], cap_l[W];
+                for (int u = 0; u < U; ++u) {
+                    have[u] = (ch + u) < nch;
+                    j0[u] = (c0 + (have[u] ? ch + u : ch)) * 32;
+                    tp[u] = ct + j0[u];
+                    for (int l = 0; l < W; ++l) { rvsum[u][l] = 0; it_l[u][l] = 0; }
+                }
+                for (int l = 0; l < W; ++l) cap_l[l] = 0;
                 for (int p = 0; p < K; ++p) {
-                    solve_planet_warp(ct + j0, wc + p * kPlanetStride, m.tol, m.itmax, v, it_l, cap_l, st);
-                    for (int l = 0; l < W; ++l) rvsum[l] = (p == 0) ? v[l] : rvsum[l] + v[l];
+                    solve_planet_warp(U, tp, wc + p * kPlanetStride, m.tol, m.itmax, v, it_l, cap_l, st);
+                    for (int u = 0; u < U; ++u)
+                        for (int l = 0; l < W; ++l) rvsum[u][l] = (p == 0) ? v[u][l] : rvsum[u][l] + v[u][l];
                 }
                 for (int l = 0; l < W; ++l) {
-                    const int j = j0 + l;
-                    const bool live = j < N;
-                    const int ii = cid[j];
-                    double rvm = ic[2 * ii];
-                    if (K > 0) rvm = rvm + rvsum[l];
-                    if (m.drift_in_model) {
-                        const double tt = ctt[j], t2 = tt * tt;
-                        double dr = dc[0] * tt;
-                        dr = dr + dc[1] * t2;
-                        dr = dr + dc[2] * (t2 * tt);
-                        dr = dr + dc[3] * (t2 * t2);
-                        rvm = rvm + dr;
+                    caps[l] += cap_l[l];
+                    for (int u = 0; u < U; ++u) {
+                        const int j = j0[u] + l;
+                        const bool live = have[u] && j < N;
+                        const int ii = cid[j];
+                        double rvm = ic[2 * ii];
+                        if (K > 0) rvm = rvm + rvsum[u][l];
+                        if (m.drift_in_model) {
+                            const double tt = ctt[j], t2 = tt * tt;
+                            double dr = dc[0] * tt;
+                            dr = dr + dc[1] * t2;
+                            dr = dr + dc[2] * (t2 * tt);
+                            dr = dr + dc[3] * (t2 * t2);
+                            rvm = rvm + dr;
+                        }
+                        for (int q = 0; q < nlin; ++q) rvm = rvm + dc[4 + q] * clin[(size_t)q * Npad + j];
+                        const double res = crv[j] - rvm;
+                        const double var = cs2[j] + ic[2 * ii + 1];
+                        const double term = (res * res) * rvl::rcp(var + var);
+                        double mant; int ex;
+                        const bool okv = rvl::split_pos(var, mant, ex);
+                        if (live) {
+                            chi[l] = chi[l] + term; prod[l] = prod[l] * mant; esum[l] += ex; ok[l] = ok[l] && okv;
+                            iters[l] += it_l[u][l];
+                        }
                     }
-                    for (int q = 0; q < nlin; ++q) rvm = rvm + dc[4 + q] * clin[(size_t)q * Npad + j];
-                    const double res = crv[j] - rvm;
-                    const double var = cs2[j] + ic[2 * ii + 1];
-                    const double term = (res * res) * rvl::rcp(var + var);
-                    double mant; int ex;
-                    const bool okv = rvl::split_pos(var, mant, ex);
-                    if (live) {
-                        chi[l] = chi[l] + term; prod[l] = prod[l] * mant; esum[l] += ex; ok[l] = ok[l] && okv;
-                        iters[l] += it_l[l]; caps[l] += cap_l[l];
-                    }
-                    if ((ch & 511) == 511) { double mm; int ee; rvl::split_pos(prod[l], mm, ee); prod[l] = mm; esum[l] += ee; }
+                    if ((ch & 255) == 254 || (ch & 255) == 255) { double mm; int ee; rvl::split_pos(prod[l], mm, ee); prod[l] = mm; esum[l] += ee; }
                 }
             }
             bool all_ok = true;
@@ -206,7 +234,7 @@ extern "C" int emul_loglike(const rvl_model_desc *mp, const double *t, const dou
             if (all_ok) {
                 for (int o = 16; o > 0; o >>= 1) {  // xor butterfly, as __shfl_xor_sync
                     double nchi[W], nprod[W]; int nes[W];
-                    if (o == 4) for (int l = 0; l < W; ++l) { double mm; int ee; rvl::split_pos(prod[l], mm, ee); prod[l] = mm; esum[l] += ee; }
+                    for (int l = 0; l < W; ++l) { double mm; int ee; rvl::split_pos(prod[l], mm, ee); prod[l] = mm; esum[l] += ee; }
                     for (int l = 0; l < W; ++l) { nchi[l] = chi[l] + chi[l ^ o]; nprod[l] = prod[l] * prod[l ^ o]; nes[l] = esum[l] + esum[l ^ o]; }
                     memcpy(chi, nchi, sizeof chi); memcpy(prod, nprod, sizeof prod); memcpy(esum, nes, sizeof esum);
                 }

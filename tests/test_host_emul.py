@@ -30,7 +30,7 @@ def emul():
     lib.emul_rcp.restype = ctypes.c_double
     lib.emul_rcp.argtypes = [ctypes.c_double]
 
-    def run(desc, om, theta, S=1):
+    def run(desc, om, theta, S=1, U=1):
         theta = np.ascontiguousarray(theta)
         out = np.empty(len(theta))
         stats = (ctypes.c_longlong * 6)()
@@ -38,21 +38,21 @@ def emul():
         lib.emul_loglike(ctypes.byref(desc), om.time.ctypes.data_as(dp), om.vrad.ctypes.data_as(dp),
                          om.svrad.ctypes.data_as(dp), ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                          len(om.time), None, theta.ctypes.data_as(dp), ctypes.c_longlong(len(theta)),
-                         S, out.ctypes.data_as(dp), stats)
+                         S, U, out.ctypes.data_as(dp), stats)
         return out, list(stats)
     run.lib = lib
     return run
 
 
-@pytest.mark.parametrize("name,S", [("cfg1", 1), ("cfg2", 1), ("cfg2", 4), ("cfg3", 1),
-                                    ("cfg5", 2), ("edge_mixed", 1)])
-def test_kernel_arithmetic_vs_reference(emul, name, S):
+@pytest.mark.parametrize("name,S,U", [("cfg1", 1, 1), ("cfg2", 1, 1), ("cfg2", 4, 2), ("cfg3", 1, 2),
+                                      ("cfg5", 2, 1), ("edge_mixed", 1, 1), ("edge_mixed", 1, 2)])
+def test_kernel_arithmetic_vs_reference(emul, name, S, U):
     meta, z = load_golden(name)
     om = oracle_model(meta, z)
     desc, _ = compile_model(meta["parnames"], meta["fixed"], meta["insts"], om.time[0])
     n = min(len(z["theta"]), 64)
     theta, want = z["theta"][:n], z["lnl"][:n]
-    got, stats = emul(desc, om, theta, S)
+    got, stats = emul(desc, om, theta, S, U)
     if name == "edge_mixed":
         # rows with e > 0.97 follow chaotic Newton trajectories: bounded by the
         # reference's own solver tolerance, not by 1e-9
