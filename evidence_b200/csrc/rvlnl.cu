@@ -296,8 +296,8 @@ __device__ __forceinline__ bool point_setup(const rvl_model_desc &m, const doubl
 // ---- the likelihood kernel ------------------------------------------------------------------
 // U = epochs per lane in flight (1: 1024 threads/SM at <=64 registers; 2: 512 threads/SM at
 // <=128 registers, two chunks of 32 epochs per warp trip).
-template <int VARIANT, int U>
-__global__ void __launch_bounds__(U == 1 ? 1024 : 512, 1) rv_lnl_kernel(const KArgs a)
+template <int VARIANT, int U, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [0,8) mbarrier | [128, 128+sizeof(model)) model | epoch columns | inst ids | warp consts
@@ -628,19 +628,18 @@ __global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *n
 }
 
 // ---- register-resident DFMA loop: the FP64 roofline denominator -------------------------------
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double *out, int iters, double a, double b)
 {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
-           x6 = x0 + 6, x7 = x0 + 7;
+    // 4 independent chains per thread, 32 warps per SM: the best of the tools/ubench.cu grid
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b);
-            x3 = __fma_rn(x3, a, b); x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b);
-            x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+        for (int u = 0; u < 16; ++u) {
+            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b);
+            x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
         }
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = (x0 + x1) + (x2 + x3);
 }
 
 thread_local std::string g_create_error;
@@ -683,7 +682,7 @@ struct rvl_handle {
     unsigned int *d_work = nullptr;            // sm_count
 
     // options
-    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1, opt_ilp = 1;
+    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1, opt_ilp = 2;
 
     // bookkeeping
     uint64_t n_points = 0, n_solves = 0, launches = 0;
@@ -794,8 +793,8 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     int wstride = m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar;
     wstride = (wstride + 1) & ~1;
     const int U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
-    int W = h->opt_warps > 0 ? h->opt_warps : (U == 2 ? 16 : 32);
-    W = std::max(1, std::min(U == 2 ? 16 : 32, W));
+    int W = h->opt_warps > 0 ? h->opt_warps : (U == 2 ? 24 : 32);
+    W = std::max(1, std::min(U == 2 ? 24 : 32, W));
     // smallest slice count whose slice fits in shared memory
     int S = 1;
     auto fits = [&](int s) {
@@ -824,12 +823,12 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     return RVL_OK;
 }
 
-template <int V, int U>
+template <int V, int U, int T>
 int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
 {
-    CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                h->smem_optin));
-    rv_lnl_kernel<V, U><<<pl.grid, pl.W * 32, pl.smem, st>>>(a);
+    rv_lnl_kernel<V, U, T><<<pl.grid, std::min(pl.W * 32, T), pl.smem, st>>>(a);
     CU(h, cudaGetLastError());
     return RVL_OK;
 }
@@ -854,9 +853,10 @@ int enqueue_loglike(rvl_t *h, const double *dTheta, long long B, double *dlnL, c
     a.S = pl.S; a.cps = pl.cps; a.wstride = pl.wstride;
     CU(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned) * (size_t)h->sm_count, st));
     if (timed) CU(h, cudaEventRecord(h->ev0, st));
-    if (h->opt_variant == 1) rc = launch_lnl_v<1, 1>(h, a, pl, st);
-    else if (pl.U == 2) rc = launch_lnl_v<0, 2>(h, a, pl, st);
-    else rc = launch_lnl_v<0, 1>(h, a, pl, st);
+    if (h->opt_variant == 1) rc = launch_lnl_v<1, 1, 1024>(h, a, pl, st);
+    else if (pl.U == 2 && pl.W <= 16) rc = launch_lnl_v<0, 2, 512>(h, a, pl, st);
+    else if (pl.U == 2) rc = launch_lnl_v<0, 2, 768>(h, a, pl, st);
+    else rc = launch_lnl_v<0, 1, 1024>(h, a, pl, st);
     if (rc) return rc;
     if (timed) { CU(h, cudaEventRecord(h->ev1, st)); h->timing_pending = true; }
     ++h->launches;
@@ -1230,7 +1230,7 @@ int rvl_fp64_peak(rvl_t *h, double *tflops)
 {
     if (!h || !tflops) return RVL_EINVAL;
     DevGuard g(h->device);
-    const int blocks = h->sm_count * 8, tb = 256, iters = 4096;
+    const int blocks = h->sm_count, tb = 1024, iters = 4096;
     double *out = nullptr;
     CU(h, cudaMalloc(&out, sizeof(double) * (size_t)blocks * tb));
     double best = 0.0;
