@@ -63,9 +63,12 @@ def test_no_cpu_fallback_without_a_gpu(built_lib):
 
 
 def test_product_never_imports_the_oracle():
+    """The checker is test infrastructure: nothing under evidence_b200/ may import, load or run it."""
     pkg = os.path.join(ROOT, "evidence_b200")
+    banned = re.compile(r"^\s*(from|import)\s+oracle\b|rv_oracle|librvoracle|oracle/_ref|oracle/_build|"
+                        r"trueanomaly\.so|#include\s+\"[^\"]*oracle", re.M)
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)
+                assert not banned.search(text), os.path.join(dirpath, f)

@@ -1,0 +1,87 @@
+"""
+CPU tests: the seeded vectorised nested sampler and the runner plumbing, on the analytic
+problems the reference's own integration tests use (tests/test_polychord.py:75-151 of the
+reference: unit Gaussian exp(-x^2/2) with U(-10,10) priors, ln Z = d ln(sqrt(2 pi)/20)
+= -2.0768 (1-D), -4.1536 (2-D), tolerance 0.5).
+"""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from evidence_b200 import priors
+from evidence_b200 import ultranest as runner
+from evidence_b200.sampler import nested_sample
+
+
+class GaussianModel:
+    """The reference's toy model protocol (tests/test_examples/gaussian/model_gaussian_example.py)."""
+
+    def __init__(self, ndim):
+        self.parnames = sorted(f"par_x{i + 1}" for i in range(ndim))
+        self.datadict, self.fixedpardict = {}, {}
+
+    def log_likelihood(self, x):
+        return -0.5 * np.sum((np.asarray(x) - 0.0) ** 2)
+
+
+@pytest.mark.parametrize("ndim,want", [(1, -2.0768), (2, -4.1536)])
+def test_analytic_gaussian_evidence(ndim, want):
+    res = nested_sample(lambda th: -0.5 * np.sum(th ** 2, axis=1), lambda u: -10 + 20 * u, ndim,
+                        nlive=400, ndraw=2048, seed=3)
+    assert abs(res.logz - want) < 0.5  # the reference's own bar
+    assert abs(res.logz - want) < 4 * res.logzerr + 0.05
+    assert res.samples.shape[1] == ndim and abs(np.mean(res.samples)) < 0.3
+
+
+def test_sampler_is_deterministic_for_a_seed():
+    f = lambda th: -0.5 * np.sum(th ** 2, axis=1)  # noqa: E731
+    g = lambda u: -10 + 20 * u  # noqa: E731
+    a = nested_sample(f, g, 2, nlive=100, ndraw=512, seed=7)
+    b = nested_sample(f, g, 2, nlive=100, ndraw=512, seed=7)
+    assert a.logz == b.logz and a.ncall == b.ncall
+    c = nested_sample(f, g, 2, nlive=100, ndraw=512, seed=8)
+    assert c.logz != a.logz
+
+
+def test_runner_output_contract(tmp_path):
+    model = GaussianModel(2)
+    priordict = {p: priors.Uniform(-10, 10) for p in model.parnames}
+    rundict = {"target": "gauss ian", "runid": "2 d", "save_dir": str(tmp_path), "nplanets": 0}
+    out = runner.run(model, rundict, priordict, {"nlive": 100, "sampler": "builtin", "seed": 5,
+                                                 "ndraw_min": 512})
+    assert abs(out.logZ + 4.1536) < 0.5
+    for attr in ("runtime", "rundict", "fixedpardict", "model_name", "nlive", "nrepeats",
+                 "isodate", "ncores", "parnames", "ndim", "sampler", "base_dir", "file_root",
+                 "logZ", "logZerr", "nlike", "samples"):
+        assert hasattr(out, attr), attr  # evidence/ultranest/__init__.py:200-229
+    assert out.file_root.startswith("gaussian_2d_k0_nlive100_ncores1_ultranest_")
+    assert list(out.samples.columns) == model.parnames
+    pkl = os.path.join(os.path.dirname(out.base_dir), out.file_root + ".pkl")
+    assert pickle.load(open(pkl, "rb"))["logZ"] == out.logZ
+
+
+def test_settings_defaults_match_the_reference():
+    s = runner.set_ultrasettings({"target": "t", "runid": "r"}, None, 7, 0, "D",
+                                 ["drift_lin", "drift_quad", "a"])
+    assert (s["nlive"], s["nsteps"], s["dlogz"], s["frac_remain"], s["num_bootstraps"]) == \
+        (175, 21, 0.5, 0.01, 30)  # :333-338
+    assert "_d2_" in s["file_root"] and s["log_dir"].endswith("ultraresults")
+    with pytest.raises(TypeError):
+        runner.set_ultrasettings({"target": "t", "runid": "r"}, [1], 7, 0, "D", [])
+
+
+def test_polychord_adapter_defaults_and_callbacks():
+    from evidence_b200 import polychord as pc
+    s = pc.default_settings(7)
+    assert s["nlive"] == 175 and s["num_repeats"] == 35 and s["do_clustering"] is True
+    assert s["precision_criterion"] == 0.001  # reference tests/test_polychord.py:47-50
+    for bad in ({"nlive": 10.5}, {"num_repeats": 1.5}, {"do_clustering": 1},
+                {"precision_criterion": 1}):
+        with pytest.raises(TypeError):
+            pc.default_settings(7, bad)
+    model = GaussianModel(2)
+    prior, loglike = pc.make_callbacks(model, {p: priors.Uniform(-10, 10) for p in model.parnames})
+    assert np.allclose(prior(np.array([0.5, 0.75])), [0.0, 5.0])
+    assert loglike(np.array([1.0, 1.0])) == (-1.0, [])
