@@ -1,5 +1,5 @@
 """
-A small, seeded, fully vectorised nested sampler.
+Small, seeded, fully vectorised nested samplers.
 
 The reference delegates sampling to third-party packages (UltraNest, PolyChord) that are not part
 of its repository and are absent from this image.  The runner in
@@ -8,14 +8,23 @@ that makes end-to-end ln Z runs possible without it, and -- because it is determ
 given seed -- lets the SAME sampler code be driven by the device likelihood and by the CPU oracle
 to check that the two agree on ln Z (BASELINE.json north_star).
 
-Algorithm: classic nested sampling (Skilling 2006) with rejection sampling from a single
-bounding ellipsoid of the live points in unit-cube space (as MultiNest's ellipsoidal mode with
-one ellipsoid / nestle's 'single' bound), enlarged by ``enlarge`` in radius.  Candidates are
-drawn and evaluated in batches of ``ndraw`` -- the large vectorised batches the device path is
-built for -- and consumed in order; a candidate drawn under an older (larger) bound is still a
-fair draw from the prior restricted to any later likelihood contour, so a batch feeds many
-iterations.  ln Z and its uncertainty follow Skilling's estimate
-sigma = sqrt(H / nlive).
+Two replacement schemes for classic nested sampling (Skilling 2006):
+
+``nested_sample`` (default, method='slice'): the k worst live points are retired per round
+(prior volume shrinks by 1/n for n = nlive, nlive-1, ..., the dynamic-live-point bookkeeping) and
+k walkers started from surviving live points take ``nsteps`` slice-sampling moves along random
+directions whitened by the live-point covariance, under the hard constraint L > L*_k -- the
+scheme of PolyChord and of UltraNest's step samplers (the reference configures UltraNest with a
+RegionSliceSampler, evidence/ultranest/__init__.py:175).  All k walkers are advanced in lock-step,
+so every likelihood call is one batch of up to k points.  Robust for the multimodal period
+posteriors of RV models.
+
+``nested_sample_ellipsoid``: rejection sampling from a single bounding ellipsoid of the live
+points (MultiNest with one ellipsoid / nestle's 'single' bound); candidates are drawn in batches
+of ``ndraw`` -- the large batches the device path is built for -- and consumed in order.  Efficient
+for unimodal problems only.
+
+ln Z uncertainty follows Skilling's estimate sigma = sqrt(H / nlive).
 """
 import numpy as np
 
@@ -52,9 +61,9 @@ def _draw_in_ellipsoid(rng, ctr, L, n):
     return ctr + (z * r[:, None]) @ L.T
 
 
-def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, frac_remain=0.01,
-                  enlarge=1.15, seed=0, max_calls=50_000_000, update_interval=None,
-                  verbose=False):
+def nested_sample_ellipsoid(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5,
+                            frac_remain=0.01, enlarge=1.15, seed=0, max_calls=50_000_000,
+                            update_interval=None, verbose=False):
     """
     loglike(theta[n, ndim]) -> lnL[n] and transform(u[n, ndim]) -> theta[n, ndim] are the
     vectorised callbacks (UltraNest's ``vectorized=True`` convention).
@@ -164,3 +173,157 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
                         ncall=int(ncall), niter=int(it), information=float(h_info),
                         samples=theta[idx], weighted_samples=theta, weights=weights,
                         logl=dead_logl, nlive=nlive, seed=seed)
+
+
+# ------------------------------------------------------------------------------------------
+# slice-sampling replacement (default)
+# ------------------------------------------------------------------------------------------
+def _whitening(u):
+    d = u.shape[1]
+    cov = np.cov(u.T).reshape(d, d) + np.eye(d) * 1e-18
+    try:
+        return np.linalg.cholesky(cov)
+    except np.linalg.LinAlgError:
+        return np.diag(np.sqrt(np.maximum(np.diag(cov), 1e-30)))
+
+
+def _slice_moves(rng, loglike, transform, u, lmin, chol, nsteps, max_expand=16, max_shrink=64):
+    """Advance k walkers u[k, d] by nsteps slice moves under L > lmin; all evaluations batched."""
+    k, d = u.shape
+    theta = transform(u)
+    lcur = np.full(k, np.nan)
+    ncall = 0
+
+    def evaluate(points, mask):
+        """lnL of points[mask] (inside the cube only); -inf elsewhere."""
+        nonlocal ncall
+        out = np.full(len(points), -np.inf)
+        th = np.zeros_like(points)
+        idx = np.where(mask & np.all((points >= 0.0) & (points < 1.0), axis=1))[0]
+        if len(idx):
+            th[idx] = transform(points[idx])
+            out[idx] = loglike(th[idx])
+            ncall += len(idx)
+        return out, th
+
+    for _ in range(nsteps):
+        z = rng.standard_normal((k, d))
+        z /= np.linalg.norm(z, axis=1, keepdims=True)
+        dirn = z @ chol.T
+        r = rng.random(k)
+        lo, hi = -r, 1.0 - r
+        for side in (0, 1):  # stepping out, one side at a time, every walker in lock-step
+            grow = np.ones(k, dtype=bool)
+            for _ in range(max_expand):
+                if not grow.any():
+                    break
+                edge = lo if side == 0 else hi
+                l_edge, _ = evaluate(u + edge[:, None] * dirn, grow)
+                grow &= l_edge > lmin
+                if side == 0:
+                    lo = np.where(grow, lo - 1.0, lo)
+                else:
+                    hi = np.where(grow, hi + 1.0, hi)
+        pending = np.ones(k, dtype=bool)
+        draws = rng.random((max_shrink, k))
+        for it in range(max_shrink):  # shrinkage
+            if not pending.any():
+                break
+            t = lo + (hi - lo) * draws[it]
+            cand = u + t[:, None] * dirn
+            l_c, th_c = evaluate(cand, pending)
+            ok = pending & (l_c > lmin)
+            u[ok], theta[ok], lcur[ok] = cand[ok], th_c[ok], l_c[ok]
+            pending &= ~ok
+            lo = np.where(pending & (t < 0), t, lo)
+            hi = np.where(pending & (t >= 0), t, hi)
+        # walkers that never found a point keep their position (the bracket collapsed)
+    return u, theta, lcur, ncall
+
+
+def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, frac_remain=0.01,
+                  seed=0, nsteps=None, batch_fraction=0.2, method="slice", max_calls=500_000_000,
+                  verbose=False, **kw):
+    """
+    Seeded vectorised nested sampling; see the module docstring.  ``loglike(theta[n, ndim])`` and
+    ``transform(u[n, ndim])`` follow UltraNest's ``vectorized=True`` convention.  Returns a
+    ``NestedResult`` (logz, logzerr, ncall, niter, samples, ...).
+    """
+    if method == "ellipsoid":
+        return nested_sample_ellipsoid(loglike, transform, ndim, nlive=nlive, ndraw=ndraw,
+                                       dlogz=dlogz, frac_remain=frac_remain, seed=seed,
+                                       max_calls=max_calls, verbose=verbose, **kw)
+    rng = np.random.default_rng(seed)
+    nsteps = nsteps or max(4, 2 * ndim)
+    k = max(1, min(int(batch_fraction * nlive), nlive - 2, ndraw))
+    u_live = rng.random((nlive, ndim))
+    th_live = transform(u_live)
+    l_live = np.asarray(loglike(th_live), dtype=np.float64).copy()
+    ncall = nlive
+    logz, h_info, logx = -np.inf, 0.0, 0.0
+    dead_theta, dead_logl, dead_logw = [], [], []
+    niter = 0
+
+    def absorb(lval, logw):
+        nonlocal logz, h_info
+        contrib = lval + logw
+        new = np.logaddexp(logz, contrib)
+        if np.isfinite(new):
+            h_info = (np.exp(contrib - new) * lval
+                      + (np.exp(logz - new) * (h_info + logz) if np.isfinite(logz) else 0.0) - new)
+        logz = new
+
+    while True:
+        order = np.argsort(l_live, kind="stable")
+        worst = order[:k]
+        n_cur = nlive
+        for j in worst:  # retire the k worst one by one: shrinkage 1/n with n = nlive, nlive-1, ...
+            logx_new = logx - 1.0 / n_cur
+            logw = logx + np.log1p(-np.exp(logx_new - logx))
+            absorb(l_live[j], logw)
+            dead_theta.append(th_live[j].copy())
+            dead_logl.append(l_live[j])
+            dead_logw.append(logw)
+            logx = logx_new
+            n_cur -= 1
+            niter += 1
+        lmin = l_live[worst[-1]]
+        keep = order[k:]
+        chol = _whitening(u_live[keep])
+        starts = keep[rng.integers(0, len(keep), k)]
+        u_new, th_new, l_new, nc = _slice_moves(rng, loglike, transform, u_live[starts].copy(),
+                                                lmin, chol, nsteps)
+        ncall += nc
+        stuck = ~np.isfinite(l_new)  # a walker that never moved is a copy of its start point
+        l_new = np.where(stuck, l_live[starts], l_new)
+        th_new[stuck] = th_live[starts][stuck]
+        u_live[worst], th_live[worst], l_live[worst] = u_new, th_new, l_new
+        if ncall > max_calls:
+            raise RuntimeError("nested_sample: max_calls exceeded")
+        log_remain = np.max(l_live) + logx
+        total = np.logaddexp(logz, log_remain)
+        if verbose and (niter // k) % 20 == 0:
+            print(f"it={niter} lnZ={logz:.3f} ln(remain/Z)={log_remain - logz:.2f} ncall={ncall}")
+        # UltraNest's two criteria (evidence/ultranest/__init__.py:181-185): remaining fraction
+        # of the evidence in the live points, and their possible ln Z contribution
+        if log_remain - total < np.log(frac_remain) and total - logz < dlogz:
+            break
+
+    logw_live = logx - np.log(nlive)
+    for j in np.argsort(l_live, kind="stable"):
+        absorb(l_live[j], logw_live)
+        dead_theta.append(th_live[j].copy())
+        dead_logl.append(l_live[j])
+        dead_logw.append(logw_live)
+    dead_logl, dead_logw = np.array(dead_logl), np.array(dead_logw)
+    logwt = dead_logl + dead_logw - logz
+    weights = np.exp(logwt - np.max(logwt))
+    weights /= weights.sum()
+    theta = np.array(dead_theta)
+    nsamp = max(1, int(1.0 / np.sum(weights ** 2)))
+    pos = (rng.random() + np.arange(nsamp)) / nsamp
+    idx = np.minimum(np.searchsorted(np.cumsum(weights), pos), len(weights) - 1)
+    return NestedResult(logz=float(logz), logzerr=float(np.sqrt(max(h_info, 0.0) / nlive)),
+                        ncall=int(ncall), niter=int(niter), information=float(h_info),
+                        samples=theta[idx], weighted_samples=theta, weights=weights,
+                        logl=dead_logl, nlive=nlive, seed=seed, method="slice")

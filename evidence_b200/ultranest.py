@@ -12,7 +12,8 @@ post-processing and pickles stay compatible.  What changes is the hot loop: the 
 Extra ``ultrasettings`` keys (the "config switch"):
     'vectorized' (True), 'ndraw_min' (4096), 'ndraw_max' (65536), 'seed' (None),
     'stepsampler' ('region-slice' like the reference | 'population-slice' | 'none'),
-    'sampler' ('auto' | 'ultranest' | 'builtin'), 'postprocess' (False), 'plot' (False)
+    'sampler' ('auto' | 'ultranest' | 'builtin'), 'builtin_method' ('slice' | 'ellipsoid'),
+    'postprocess' (False), 'plot' (False)
 
 UltraNest is a third-party package that is not part of the reference repository.
 When it is importable it is used; otherwise -- or with ``'sampler': 'builtin'`` -- the seeded
@@ -121,7 +122,8 @@ def run(model, rundict, priordict, ultrasettings=None):
         os.makedirs(settings["log_dir"], exist_ok=True)
         res = nested_sample(loglike, prior, ndim, nlive=settings["nlive"],
                             ndraw=settings["ndraw_min"], dlogz=settings["dlogz"],
-                            frac_remain=settings["frac_remain"],
+                            frac_remain=settings["frac_remain"], nsteps=settings["nsteps"],
+                            method=settings["builtin_method"],
                             seed=0 if settings["seed"] is None else settings["seed"])
         logz, logzerr, ncall, samples = res.logz, res.logzerr, res.ncall, res.samples
         name = "b200-nested"
@@ -186,8 +188,8 @@ def set_ultrasettings(rundict, ultrasettings, ndim, nderived, isodate, parnames)
                 "num_bootstraps": 30,
                 # the device-path switch
                 "vectorized": True, "ndraw_min": 4096, "ndraw_max": 65536, "seed": None,
-                "stepsampler": "region-slice", "sampler": "auto", "postprocess": False,
-                "plot": False}
+                "stepsampler": "region-slice", "sampler": "auto", "builtin_method": "slice",
+                "postprocess": False, "plot": False}
     if ultrasettings is not None:
         if type(ultrasettings) is not dict:
             raise TypeError("ultrasettings has to be a dictionary")

@@ -26,10 +26,11 @@ class GaussianModel:
         return -0.5 * np.sum((np.asarray(x) - 0.0) ** 2)
 
 
+@pytest.mark.parametrize("method", ["slice", "ellipsoid"])
 @pytest.mark.parametrize("ndim,want", [(1, -2.0768), (2, -4.1536)])
-def test_analytic_gaussian_evidence(ndim, want):
+def test_analytic_gaussian_evidence(ndim, want, method):
     res = nested_sample(lambda th: -0.5 * np.sum(th ** 2, axis=1), lambda u: -10 + 20 * u, ndim,
-                        nlive=400, ndraw=2048, seed=3)
+                        nlive=400, ndraw=2048, seed=3, method=method)
     assert abs(res.logz - want) < 0.5  # the reference's own bar
     assert abs(res.logz - want) < 4 * res.logzerr + 0.05
     assert res.samples.shape[1] == ndim and abs(np.mean(res.samples)) < 0.3
