@@ -133,6 +133,15 @@ constexpr int kHiTrigMax = 0x40F86A00;  // 1e5 = 0x40F86A0000000000: |x| < 1e5  
 constexpr int kHiTiny = 0x3F500000;     // abs_hi(d) <  this  <=>  |d| <  2^-10
 constexpr int kHiSmall = 0x3FA00000;    // abs_hi(d) <  this  <=>  |d| <  2^-5
 
+template <int U>
+__device__ __forceinline__ bool any_big(const double (&E)[U])
+{
+    int emax = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) emax = max(emax, abs_hi(E[u]));
+    return __any_sync(kFull, !(emax < kHiTrigMax));
+}
+
 // ---- U epochs per lane x one planet: Kepler solves + RV terms -------------------------------
 // VARIANT 0: optimised (reciprocal-multiply Newton step, warp-uniform small-step sin/cos
 //            advance).  VARIANT 1: conservative (IEEE division, full sin/cos every step) — kept
@@ -187,7 +196,7 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         }
         if (!__any_sync(kFull, any_left)) break;
         ++trip;
-        int hmax = 0, emax = 0;
+        int hmax = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             double En;
@@ -203,7 +212,6 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
             E[u] = En;
             last[u] = pa[u] ? trip : last[u];
             hmax = max(hmax, abs_hi(d[u]));
-            emax = max(emax, abs_hi(En));
         }
         if (VARIANT == 0 && __all_sync(kFull, hmax < kHiTiny)) {
 #pragma unroll
@@ -211,7 +219,7 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         } else if (VARIANT == 0 && __all_sync(kFull, hmax < kHiSmall)) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_small(d[u], s[u], c[u]);
-        } else if (slow || (trip > 2 && __any_sync(kFull, !(emax < kHiTrigMax)))) {
+        } else if (slow || (trip > 2 && any_big<U>(E))) {
             // |E| can only leave the fast range after >= 3 Newton steps (|step| <= 100 |f|)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -265,7 +273,13 @@ __device__ __forceinline__ bool point_setup(const rvl_model_desc &m, const doubl
         if (pl.phase_mode == RVL_PHASE_ML0) M0 = rvl::sub(M0, omega);
         const double ec = ecc > 0.99 ? 0.99 : ecc;  // trueanomaly.c:11-12
         double sw, cw;
-        sincos(omega, &sw, &cw);
+        if (abs_hi(omega) < kHiTrigMax) {
+            rvl::sincos_fast(omega, sw, cw);
+        } else {
+            const double2 r = sincos_slow(omega);
+            sw = r.x;
+            cw = r.y;
+        }
         const double root = sqrt(rvl::mul(rvl::sub(1.0, ec), rvl::add(1.0, ec)));
         double *pc = wc + lane * kPlanetStride;
         pc[0] = __ddiv_rn(6.283185307179586, per);  // 2*np.pi/P_day (:459)
@@ -343,6 +357,9 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     const double tol = m.tol;
     const int itmax = m.itmax;
     const bool has_drift = m.drift_in_model != 0;
+    int drift_hi = 0;  // highest drift coefficient that is a parameter or a non-zero constant
+    for (int i = 1; i < 4; ++i)
+        if (m.drift[i].slot >= 0 || m.drift[i].value != 0.0) drift_hi = i;
     const int nlin = m.n_linpar;
     double *wc = wconst + (size_t)warp * a.wstride;
     // 32-bit shared-window addresses of everything the hot loop reads
@@ -405,12 +422,19 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
                     double rvm = lds_f64(ai);
                     if (K > 0) rvm = rvl::add(rvm, rvsum[u]);
                     if (has_drift) {
+                        // lin*tt + quad*tt^2 + cub*tt^3 + quar*tt^4, left to right (:271); a
+                        // coefficient that is absent from the model is an exact +0 term: skipped
                         const double tt = lds_f64(ae + 3u * colb);
-                        const double t2 = rvl::mul(tt, tt);
                         double dr = rvl::mul(lds_f64(a_dc), tt);
-                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 8), t2));
-                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 16), rvl::mul(t2, tt)));
-                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 24), rvl::mul(t2, t2)));
+                        if (drift_hi > 0) {
+                            const double t2 = rvl::mul(tt, tt);
+                            dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 8), t2));
+                            if (drift_hi > 1) {
+                                dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 16), rvl::mul(t2, tt)));
+                                if (drift_hi > 2)
+                                    dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 24), rvl::mul(t2, t2)));
+                            }
+                        }
                         rvm = rvl::add(rvm, dr);
                     }
                     for (int l = 0; l < nlin; ++l)
@@ -445,19 +469,19 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
         if (valid) {
             const bool all_ok = __all_sync(kFull, ok);
             if (all_ok) {
+                {  // every lane's mantissa product back to [1,2): 32 of them multiply to < 2^32
+                    double mm;
+                    int ee;
+                    rvl::split_pos(prod, mm, ee);
+                    prod = mm;
+                    esum += ee;
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     chi = rvl::add(chi, __shfl_xor_sync(kFull, chi, o));
-                    {  // renormalise the mantissa product to [1,2) before every pairing
-                        double mm;
-                        int ee;
-                        rvl::split_pos(prod, mm, ee);
-                        prod = mm;
-                        esum += ee;
-                    }
                     prod = rvl::mul(prod, __shfl_xor_sync(kFull, prod, o));
-                    esum += __shfl_xor_sync(kFull, esum, o);
                 }
+                esum = __reduce_add_sync(kFull, esum);
                 // sum ln sqrt(var) = 0.5 (ln prod + esum ln 2)
                 const double ld = rvl::fma_((double)esum, rvl::kLn2Hi,
                                            rvl::fma_((double)esum, rvl::kLn2Lo, log(prod)));
@@ -482,13 +506,8 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
                 S1 = acc;
             }
             S2 = chi;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                iters += __shfl_xor_sync(kFull, iters, o);
-                caps += __shfl_xor_sync(kFull, caps, o);
-            }
-            tot_iters += (unsigned long long)iters;
-            tot_caps += (unsigned long long)caps;
+            tot_iters += (unsigned long long)__reduce_add_sync(kFull, iters);
+            tot_caps += (unsigned long long)__reduce_add_sync(kFull, caps);
         } else {
             S1 = 0.0;
             S2 = 0.0;

@@ -119,7 +119,9 @@ bool point_setup(const rvl_model_desc &m, const double *row, double *wc)
         double M0 = par_of(pl.phase, row);
         if (pl.phase_mode == RVL_PHASE_ML0) M0 = M0 - omega;
         const double ec = ecc > 0.99 ? 0.99 : ecc;
-        const double sw = sin(omega), cw = cos(omega);
+        double sw, cw;
+        if (abs_hi(omega) < kHiTrigMax) rvl::sincos_fast(omega, sw, cw);
+        else { sw = sin(omega); cw = cos(omega); }
         const double root = sqrt((1.0 - ec) * (1.0 + ec));
         double *pc = wc + p * kPlanetStride;
         pc[0] = 6.283185307179586 / per;
@@ -232,12 +234,13 @@ extern "C" int emul_loglike(const rvl_model_desc *mp, const double *t, const dou
             for (int l = 0; l < W; ++l) all_ok = all_ok && ok[l];
             double S1;
             if (all_ok) {
+                for (int l = 0; l < W; ++l) { double mm; int ee; rvl::split_pos(prod[l], mm, ee); prod[l] = mm; esum[l] += ee; }
                 for (int o = 16; o > 0; o >>= 1) {  // xor butterfly, as __shfl_xor_sync
-                    double nchi[W], nprod[W]; int nes[W];
-                    for (int l = 0; l < W; ++l) { double mm; int ee; rvl::split_pos(prod[l], mm, ee); prod[l] = mm; esum[l] += ee; }
-                    for (int l = 0; l < W; ++l) { nchi[l] = chi[l] + chi[l ^ o]; nprod[l] = prod[l] * prod[l ^ o]; nes[l] = esum[l] + esum[l ^ o]; }
-                    memcpy(chi, nchi, sizeof chi); memcpy(prod, nprod, sizeof prod); memcpy(esum, nes, sizeof esum);
+                    double nchi[W], nprod[W];
+                    for (int l = 0; l < W; ++l) { nchi[l] = chi[l] + chi[l ^ o]; nprod[l] = prod[l] * prod[l ^ o]; }
+                    memcpy(chi, nchi, sizeof chi); memcpy(prod, nprod, sizeof prod);
                 }
+                { int tot = 0; for (int l = 0; l < W; ++l) tot += esum[l]; for (int l = 0; l < W; ++l) esum[l] = tot; }
                 const double ld = fma((double)esum[0], rvl::kLn2Hi, fma((double)esum[0], rvl::kLn2Lo, log(prod[0])));
                 S1 = 0.5 * ld;
             } else {

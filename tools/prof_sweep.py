@@ -11,11 +11,15 @@ ilp = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 m.set_option("ilp", ilp)
 if len(sys.argv) > 4:
     m.set_option("warps", int(sys.argv[4]))
+if len(sys.argv) > 5:
+    m.set_option("slices", int(sys.argv[5]))
 th = torch.from_numpy(case.draw_theta(B, seed=77)).cuda()
 out = torch.empty(B, dtype=torch.float64, device='cuda')
-for _ in range(3):
+ms = []
+for _ in range(8):
     m.log_likelihood_device(th, out=out)
-    print(m.last_kernel_ms())
+    ms.append(m.last_kernel_ms())
+print(ms)
 torch.cuda.synchronize()
 c = m.counters()
-print("cfg", cfg, "B", B, "ilp", ilp, "iters/solve", c["n_newton_iters"]/c["n_solves"], "lnL/s", B/(m.last_kernel_ms()*1e-3))
+print("cfg", cfg, "B", B, "ilp", ilp, "iters/solve", c["n_newton_iters"]/c["n_solves"], "best_ms", min(ms), "lnL/s", B/(min(ms)*1e-3), "args", sys.argv[1:])
