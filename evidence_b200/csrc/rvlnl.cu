@@ -132,6 +132,7 @@ __device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7
 constexpr int kHiTrigMax = 0x40F86A00;  // 1e5 = 0x40F86A0000000000: |x| < 1e5  <=>  abs_hi < this
 constexpr int kHiTiny = 0x3F500000;     // abs_hi(d) <  this  <=>  |d| <  2^-10
 constexpr int kHiSmall = 0x3FA00000;    // abs_hi(d) <  this  <=>  |d| <  2^-5
+constexpr int kHiMedium = 0x3FE80000;   // abs_hi(d) <  this  <=>  |d| <  0.75
 
 template <int U>
 __device__ __forceinline__ bool any_big(const double (&E)[U])
@@ -166,59 +167,30 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         M[u] = rvl::mean_anomaly(nmot, t[u], epoch, M0);
         E[u] = M[u];
         big = big || !(abs_hi(M[u]) < kHiTrigMax);
-        d[u] = 1e300;  // "not yet converged"
+        d[u] = 1e300;  // "no step taken yet": forces the full sin/cos on the first pass
+        s[u] = 0.0;
+        c[u] = 1.0;
         last[u] = 0;
     }
     // slow: some |M| >= 1e5 (or non-finite), or an eccentricity outside [-0.99, 0.99] (only
     // reachable with a nonsensical direct `ecc`): every sin/cos of this solve goes through
     // libdevice, which is valid for any argument
     const bool slow = __any_sync(kFull, big || !(ec >= -0.99));
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (slow) {
-            const double2 r = sincos_slow(E[u]);
-            s[u] = r.x;
-            c[u] = r.y;
-        } else {
-            rvl::sincos_fast(E[u], s[u], c[u]);
-        }
-    }
-    int trip = 0;  // warp-uniform
-    bool any_left;
+    int trip = 0;  // warp-uniform number of Newton steps taken so far
     for (;;) {
-        bool pa[U];
-        any_left = false;
-        const bool room = trip < itmax;  // trueanomaly.c:32-33 (lanes still active hit the cap)
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            pa[u] = (fabs(d[u]) > tol) && room;  // trueanomaly.c:21
-            any_left = any_left || pa[u];
-        }
-        if (!__any_sync(kFull, any_left)) break;
-        ++trip;
+        // (1) bring (sin E, cos E) up to date with the step d just taken
         int hmax = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            double En;
-            if (VARIANT == 0) {
-                rvl::newton_step(E[u], s[u], c[u], M[u], ec, En);
-            } else {
-                const double f = rvl::sub(rvl::sub(E[u], rvl::mul(ec, s[u])), M[u]);
-                const double fp = rvl::sub(1.0, rvl::mul(ec, c[u]));
-                En = rvl::sub(E[u], __ddiv_rn(f, fp));
-            }
-            En = pa[u] ? En : E[u];
-            d[u] = rvl::sub(En, E[u]);  // exact; 0 for frozen lanes
-            E[u] = En;
-            last[u] = pa[u] ? trip : last[u];
-            hmax = max(hmax, abs_hi(d[u]));
-        }
+        for (int u = 0; u < U; ++u) hmax = max(hmax, abs_hi(d[u]));
         if (VARIANT == 0 && __all_sync(kFull, hmax < kHiTiny)) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_tiny(d[u], s[u], c[u]);
         } else if (VARIANT == 0 && __all_sync(kFull, hmax < kHiSmall)) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_small(d[u], s[u], c[u]);
+        } else if (VARIANT == 0 && !slow && __all_sync(kFull, hmax < kHiMedium)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvl::advance_medium(d[u], s[u], c[u]);
         } else if (slow || (trip > 2 && any_big<U>(E))) {
             // |E| can only leave the fast range after >= 3 Newton steps (|step| <= 100 |f|)
 #pragma unroll
@@ -230,6 +202,31 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::sincos_fast(E[u], s[u], c[u]);
+        }
+        // (2) which lanes still iterate (trueanomaly.c:21); the cap (:32-33) bounds the loop
+        bool pa[U], any_left = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pa[u] = fabs(d[u]) > tol;
+            any_left = any_left || pa[u];
+        }
+        if (trip >= itmax || !__any_sync(kFull, any_left)) break;
+        ++trip;
+        // (3) one Newton step for the active lanes; a frozen lane's step is exactly 0
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double En;
+            if (VARIANT == 0) {
+                rvl::newton_step(E[u], s[u], c[u], M[u], ec, En);
+            } else {
+                const double f = rvl::sub(rvl::sub(E[u], rvl::mul(ec, s[u])), M[u]);
+                const double fp = rvl::sub(1.0, rvl::mul(ec, c[u]));
+                En = rvl::sub(E[u], __ddiv_rn(f, fp));
+            }
+            En = pa[u] ? En : E[u];
+            d[u] = rvl::sub(En, E[u]);  // exact
+            E[u] = En;
+            last[u] = pa[u] ? trip : last[u];
         }
     }
     const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
@@ -647,18 +644,26 @@ __global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *n
 }
 
 // ---- register-resident DFMA loop: the FP64 roofline denominator -------------------------------
-__global__ void __launch_bounds__(1024) dfma_peak_kernel(double *out, int iters, double a, double b)
+template <int R>
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double *out, int iters, double, double b)
 {
-    // 4 independent chains per thread, 32 warps per SM: the best of the tools/ubench.cu grid
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    // R independent chains per thread, 32 warps per SM (grid of tools/ubench.cu)
+    double x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = threadIdx.x + r;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b);
-            x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            // multiplier from the constant bank (uniform-register operand), addend in a
+            // register: the operand form that reached the highest rate in tools/ubench.cu
+            for (int r = 0; r < R; ++r) x[r] = __fma_rn(x[r], RVL_K(23), b);
         }
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = (x0 + x1) + (x2 + x3);
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s += x[r];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 thread_local std::string g_create_error;
@@ -1249,20 +1254,23 @@ int rvl_fp64_peak(rvl_t *h, double *tflops)
 {
     if (!h || !tflops) return RVL_EINVAL;
     DevGuard g(h->device);
-    const int blocks = h->sm_count, tb = 1024, iters = 4096;
+    const int blocks = h->sm_count, tb = 1024, iters = 4000;
     double *out = nullptr;
     CU(h, cudaMalloc(&out, sizeof(double) * (size_t)blocks * tb));
     double best = 0.0;
-    for (int rep = 0; rep < 6; ++rep) {
+    for (int rep = 0; rep < 9; ++rep) {  // best over chain counts 2, 4, 8 and repetitions
+        const int R = rep % 3 == 0 ? 2 : (rep % 3 == 1 ? 4 : 8);
         CU(h, cudaEventRecord(h->ev0, h->stream));
-        dfma_peak_kernel<<<blocks, tb, 0, h->stream>>>(out, iters, 0.999999, 1e-9);
+        if (R == 2) dfma_peak_kernel<2><<<blocks, tb, 0, h->stream>>>(out, iters, 0.999999, 1e-9);
+        else if (R == 4) dfma_peak_kernel<4><<<blocks, tb, 0, h->stream>>>(out, iters, 0.999999, 1e-9);
+        else dfma_peak_kernel<8><<<blocks, tb, 0, h->stream>>>(out, iters, 0.999999, 1e-9);
         CU(h, cudaEventRecord(h->ev1, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         ++h->launches;
         float ms = 0.f;
         CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * tb;
-        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        const double flops = 2.0 * 8.0 * R * (double)iters * (double)blocks * tb;
+        if (rep >= 3) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     cudaFree(out);
     *tflops = best;

@@ -24,14 +24,14 @@ constexpr int W = 32;
 constexpr int kPlanetStride = 8;
 
 struct Stats {
-    long long trips_full, trips_small, trips_tiny, solves_warp, newton_iters, caps;
+    long long trips_full, trips_small, trips_tiny, solves_warp, newton_iters, caps, trips_medium;
 };
 
 inline double par_of(const rvl_param &p, const double *row) { return p.slot >= 0 ? row[p.slot] : p.value; }
 
 
 inline int abs_hi(double x) { return rvl::hi32(x) & 0x7fffffff; }
-constexpr int kHiTrigMax = 0x40F86A00, kHiTiny = 0x3F500000, kHiSmall = 0x3FA00000;
+constexpr int kHiTrigMax = 0x40F86A00, kHiTiny = 0x3F500000, kHiSmall = 0x3FA00000, kHiMedium = 0x3FE80000;
 
 // one planet for U chunks of 32 epochs (U*32 solves) in lock-step: mirrors solve_planet<0, U>
 void solve_planet_warp(int U, const double *const *t, const double *pc, double tol, int itmax,
@@ -47,42 +47,26 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
             E[u][l] = M[u][l];
             big = big || !(abs_hi(M[u][l]) < kHiTrigMax);
             d[u][l] = 1e300;
+            s[u][l] = 0.0;
+            c[u][l] = 1.0;
             last[u][l] = 0;
         }
     const bool slow = big || !(ec >= -0.99);
-    for (int u = 0; u < U; ++u)
-        for (int l = 0; l < W; ++l) {
-            if (slow) { s[u][l] = sin(E[u][l]); c[u][l] = cos(E[u][l]); }
-            else rvl::sincos_fast(E[u][l], s[u][l], c[u][l]);
-        }
     ++st.solves_warp;
     int trip = 0;
     for (;;) {
-        bool pa[2][W], any_left = false;
-        const bool room = trip < itmax;
+        bool all_tiny = true, all_small = true, all_medium = true, any_big = false;
         for (int u = 0; u < U; ++u)
             for (int l = 0; l < W; ++l) {
-                pa[u][l] = (fabs(d[u][l]) > tol) && room;
-                any_left = any_left || pa[u][l];
-            }
-        if (!any_left) break;
-        ++trip;
-        bool all_tiny = true, all_small = true, any_big = false;
-        for (int u = 0; u < U; ++u)
-            for (int l = 0; l < W; ++l) {
-                double En;
-                rvl::newton_step(E[u][l], s[u][l], c[u][l], M[u][l], ec, En);
-                En = pa[u][l] ? En : E[u][l];
-                d[u][l] = En - E[u][l];
-                E[u][l] = En;
-                last[u][l] = pa[u][l] ? trip : last[u][l];
                 const int h = abs_hi(d[u][l]);
                 all_tiny = all_tiny && (h < kHiTiny);
                 all_small = all_small && (h < kHiSmall);
-                any_big = any_big || !(abs_hi(En) < kHiTrigMax);
+                all_medium = all_medium && (h < kHiMedium);
+                any_big = any_big || !(abs_hi(E[u][l]) < kHiTrigMax);
             }
         if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(d[u][l], s[u][l], c[u][l]); }
         else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(d[u][l], s[u][l], c[u][l]); }
+        else if (!slow && all_medium) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_medium(d[u][l], s[u][l], c[u][l]); }
         else {
             ++st.trips_full;
             const bool lib = slow || (trip > 2 && any_big);
@@ -92,6 +76,23 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
                     else rvl::sincos_fast(E[u][l], s[u][l], c[u][l]);
                 }
         }
+        bool pa[2][W], any_left = false;
+        for (int u = 0; u < U; ++u)
+            for (int l = 0; l < W; ++l) {
+                pa[u][l] = fabs(d[u][l]) > tol;
+                any_left = any_left || pa[u][l];
+            }
+        if (trip >= itmax || !any_left) break;
+        ++trip;
+        for (int u = 0; u < U; ++u)
+            for (int l = 0; l < W; ++l) {
+                double En;
+                rvl::newton_step(E[u][l], s[u][l], c[u][l], M[u][l], ec, En);
+                En = pa[u][l] ? En : E[u][l];
+                d[u][l] = En - E[u][l];
+                E[u][l] = En;
+                last[u][l] = pa[u][l] ? trip : last[u][l];
+            }
     }
     for (int u = 0; u < U; ++u)
         for (int l = 0; l < W; ++l) {
@@ -267,6 +268,7 @@ extern "C" int emul_loglike(const rvl_model_desc *mp, const double *t, const dou
     if (stats_out) {
         stats_out[0] = st.trips_full; stats_out[1] = st.trips_small; stats_out[2] = st.trips_tiny;
         stats_out[3] = st.solves_warp; stats_out[4] = st.newton_iters; stats_out[5] = st.caps;
+        stats_out[6] = st.trips_medium;
     }
     free(ct); free(cid);
     return 0;

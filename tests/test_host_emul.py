@@ -33,7 +33,7 @@ def emul():
     def run(desc, om, theta, S=1, U=1):
         theta = np.ascontiguousarray(theta)
         out = np.empty(len(theta))
-        stats = (ctypes.c_longlong * 6)()
+        stats = (ctypes.c_longlong * 8)()
         ids = np.ascontiguousarray(om.inst_id, dtype=np.int32)
         lib.emul_loglike(ctypes.byref(desc), om.time.ctypes.data_as(dp), om.vrad.ctypes.data_as(dp),
                          om.svrad.ctypes.data_as(dp), ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
