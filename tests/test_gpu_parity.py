@@ -237,3 +237,84 @@ def test_error_reporting():
     with pytest.raises(DeviceError):
         m.set_option("no_such_option", 1)
     m.close()
+
+
+def _random_model(rng, n_epochs, n_planets, n_inst, drift_order, n_linpar):
+    """A random model + data + theta batch at the limits of the layout, in plain dicts."""
+    t = np.sort(rng.uniform(50000.0, 56000.0, n_epochs))
+    inst = np.sort(rng.integers(0, n_inst, n_epochs))
+    inst[:n_inst] = np.arange(n_inst)[: len(inst[:n_inst])]  # every instrument has >= 1 epoch
+    inst = np.sort(inst)
+    names_i = [f"i{k:02d}" for k in range(n_inst)]
+    dd = {}
+    for k, nm in enumerate(names_i):
+        msk = inst == k
+        dd[nm] = {"data": {"jdb": t[msk], "vrad": rng.normal(0, 6, msk.sum()),
+                           "svrad": rng.uniform(0.5, 2.0, msk.sum())}}
+    free, fixed, lo, hi = [], {}, {}, {}
+
+    def add(name, a, b):
+        free.append(name); lo[name] = a; hi[name] = b
+    for p in range(1, n_planets + 1):
+        add(f"planet{p}_k1", 0, 10); add(f"planet{p}_period", 1.5, 800)
+        add(f"planet{p}_ecc", 0, 0.9); add(f"planet{p}_omega", 0, 2 * np.pi)
+        add(f"planet{p}_ma0", 0, 2 * np.pi)
+        fixed[f"planet{p}_epoch"] = 53000.0 + p
+    for nm in names_i:
+        add(f"{nm}_offset", -5, 5); add(f"{nm}_jitter", 0.1, 5)
+    for nm in ("lin", "quad", "cub", "quar")[:drift_order]:
+        add(f"drift_{nm}", -0.5, 0.5)
+    lin = {f"act{j}": rng.normal(0, 1, n_epochs) for j in range(n_linpar)}
+    for nm in lin:
+        add(f"linpar_{nm}", -2, 2)
+    return dd, free, fixed, lo, hi, lin
+
+
+@pytest.mark.parametrize("shape", [
+    dict(n_epochs=20000, n_planets=2, n_inst=3, drift_order=0, n_linpar=0, B=48),   # > 1 smem slice
+    dict(n_epochs=300, n_planets=8, n_inst=16, drift_order=4, n_linpar=2, B=96),    # layout limits
+    dict(n_epochs=1, n_planets=1, n_inst=1, drift_order=1, n_linpar=0, B=40),       # single epoch
+    dict(n_epochs=33, n_planets=3, n_inst=2, drift_order=2, n_linpar=1, B=40),      # ragged chunk
+    dict(n_epochs=64, n_planets=0, n_inst=2, drift_order=3, n_linpar=1, B=40),      # no planets
+])
+def test_shapes_at_the_limits_vs_c_oracle(shape):
+    from evidence_b200.rvmodel import RVModel
+    from oracle import rv_oracle
+    rng = np.random.default_rng(shape["n_epochs"] + shape["n_planets"])
+    B = shape.pop("B")
+    dd, free, fixed, lo, hi, lin = _random_model(rng, **shape)
+    m = RVModel(fixed, dd, free, linpar_dict=lin)
+    theta = np.stack([rng.uniform(lo[p], hi[p], B) for p in m.parnames], axis=1)
+    t = np.concatenate([dd[k]["data"]["jdb"] for k in dd])
+    v = np.concatenate([dd[k]["data"]["vrad"] for k in dd])
+    s = np.concatenate([dd[k]["data"]["svrad"] for k in dd])
+    ids = np.concatenate([np.full(len(dd[k]["data"]["jdb"]), i, dtype=np.int32) for i, k in enumerate(dd)])
+    want, _, caps = rv_oracle.c_loglike_batch(m.desc_bytes(), t, v, s, ids, len(dd), theta,
+                                              linpar_cols=[lin[k] for k in lin])
+    for ilp in (1, 2):
+        m.set_option("ilp", ilp)
+        got = m.log_likelihood_batch(theta)
+        ok, worst = lnl_close(got, want)
+        assert ok, (shape, ilp, worst)
+    assert caps == 0
+    m.close()
+
+
+def test_degenerate_variance_falls_back_to_plain_logs():
+    """svrad = 0 and jitter = 0 for one epoch: var = 0 -> the reference gives inf/nan; so do we."""
+    from evidence_b200.rvmodel import RVModel
+    from oracle.rv_oracle import OracleRVModel
+    t = np.linspace(0, 10, 40)
+    err = np.ones(40); err[7] = 0.0
+    dd = lambda: {"a": {"data": {"rjd": t.copy(), "vrad": np.sin(t), "svrad": err.copy()}}}  # noqa: E731
+    names = ["a_jitter", "a_offset"]
+    m = RVModel({}, dd(), names)
+    om = OracleRVModel({}, dd(), names)
+    theta = np.array([[0.0, 0.1], [0.5, 0.1], [1e-200, 0.0]])
+    got = m.log_likelihood_batch(theta)
+    with np.errstate(all="ignore"):
+        want = om.log_likelihood_batch(theta)
+    assert np.isfinite(got[1]) and abs(got[1] - want[1]) < 1e-9
+    for g, w in ((got[0], want[0]), (got[2], want[2])):
+        assert (np.isnan(g) and np.isnan(w)) or g == w or (not np.isfinite(g) and not np.isfinite(w))
+    m.close()
