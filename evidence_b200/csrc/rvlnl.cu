@@ -583,6 +583,16 @@ __device__ __forceinline__ double ppf_eval(const rvl_prior_desc &pr, const doubl
         int k = max(1, min(pr.table_len - 1, lo));
         const double x0 = __ldg(x + k - 1), x1 = __ldg(x + k);
         const double c0 = __ldg(cdf + k - 1), c1 = __ldg(cdf + k);
+        if (p1 != 0.0) {  // p1 = 1: slopes dx/dq follow the knots -> cubic Hermite segment
+            const double *mk = x + pr.table_len;
+            const double m0 = __ldg(mk + k - 1), m1 = __ldg(mk + k);
+            if (m0 > 0.0 && m1 > 0.0) {
+                const double h = c1 - c0, t = (q - c0) / h, t2 = t * t, t3 = t2 * t;
+                const double h00 = 2.0 * t3 - 3.0 * t2 + 1.0, h10 = t3 - 2.0 * t2 + t;
+                const double h01 = -2.0 * t3 + 3.0 * t2, h11 = t3 - t2;
+                return h00 * x0 + h10 * h * m0 + h01 * x1 + h11 * h * m1;
+            }
+        }
         const double slope = __ddiv_rn(rvl::sub(x1, x0), rvl::sub(c1, c0));
         const double y = rvl::add(rvl::mul(slope, rvl::sub(q, c0)), x0);
         return p0 != 0.0 ? exp10(y) : y;  // p0 = 1: Log10Normal, 10**interp (priors.py:144)
@@ -1062,7 +1072,7 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
         if (p.kind < 0 || p.kind > RVL_PRIOR_TABLE) return fail(h, RVL_EINVAL, "unknown prior kind");
         if (p.kind == RVL_PRIOR_TABLE &&
             (p.table_len < 2 || p.table_offset < 0 || !tables ||
-             p.table_offset + 2LL * p.table_len > n_table_doubles))
+             p.table_offset + (p.p[1] != 0.0 ? 3LL : 2LL) * p.table_len > n_table_doubles))
             return fail(h, RVL_EINVAL, "prior table out of bounds");
     }
     DevGuard g(h->device);

@@ -114,7 +114,8 @@ typedef struct {
 #define RVL_PRIOR_NORMAL 5      /* p0=loc p1=scale : loc + scale ndtri(q)  (stats.norm, :436) */
 #define RVL_PRIOR_LOGNORMAL 6   /* p0=s p1=loc p2=scale : loc + scale exp(s ndtri(q)) (:437)  */
 #define RVL_PRIOR_TABLE 7       /* piecewise-linear inverse CDF through (cdf_k, x_k) knots
-                                   (p0 = 1: result is 10**interp, Log10Normal :144),
+                                   (p0 = 1: result is 10**interp, Log10Normal :144;
+                                    p1 = 1: a third array of slopes dx/dq follows -> cubic Hermite),
                                    the scheme of the interp1d priors (:118-124,195-202,223-228,
                                    282-287,321-326,349-354); also used for Beta/Gamma/Alpha */
 
@@ -122,7 +123,7 @@ typedef struct {
     int32_t kind;
     int32_t table_len;    /* RVL_PRIOR_TABLE: number of knots */
     int64_t table_offset; /* RVL_PRIOR_TABLE: offset (in doubles) of the knots inside `tables`:
-                             cdf[0..len) followed by x[0..len) */
+                             cdf[0..len) followed by x[0..len) [and slope[0..len) when p1 = 1] */
     double p[4];
 } rvl_prior_desc;
 

@@ -212,10 +212,12 @@ def test_prior_transform_vs_reference():
             want = z["ppf"][lo + j]
             ok = np.isfinite(want)
             if s["name"] in ("Alpha", "Beta", "Gamma"):
-                # dense inverse-CDF table with linear interpolation: stated tolerance 1e-3 of the
-                    # value inside [0.01, 0.99] (lnL parity is defined on identical theta)
-                    inner = ok & (q >= 0.01) & (q <= 0.99)
-                    assert np.allclose(got[inner, j], want[inner], rtol=1e-3, atol=1e-9), s
+                # inverse-CDF table + exact slopes, cubic Hermite: stated tolerance 1e-9 of the value
+                    # inside [1e-3, 1-1e-3], 1e-6 further out (lnL parity is defined on identical theta)
+                    inner = ok & (q >= 1e-3) & (q <= 1 - 1e-3)
+                    assert np.allclose(got[inner, j], want[inner], rtol=1e-9, atol=1e-12), (s, got[inner, j] / want[inner] - 1)
+                    outer = ok & (q >= 1e-6) & (q <= 1 - 1e-6)
+                    assert np.allclose(got[outer, j], want[outer], rtol=1e-6, atol=1e-12), s
             else:
                 assert np.allclose(got[ok, j], want[ok], rtol=4e-15, atol=1e-15), (s, got[ok, j] - want[ok])
         # fused transform + likelihood is the same arithmetic as the two calls

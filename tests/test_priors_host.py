@@ -43,6 +43,7 @@ def test_device_descriptors_pack_tables():
     descs, tables = priors.device_descriptors(prs)
     assert descs[0].kind == 0 and descs[1].kind == descs[2].kind == 7
     assert descs[1].table_offset == 0 and descs[2].table_offset == 2 * descs[1].table_len
-    assert tables.size == 2 * (descs[1].table_len + descs[2].table_len)
+    assert tables.size == 2 * descs[1].table_len + 3 * descs[2].table_len  # Beta ships slopes too
+    assert descs[2].p[1] == 1.0 and descs[1].p[1] == 0.0
     cdf = tables[descs[2].table_offset: descs[2].table_offset + descs[2].table_len]
     assert np.all(np.diff(cdf) > 0)

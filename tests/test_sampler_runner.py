@@ -86,3 +86,14 @@ def test_polychord_adapter_defaults_and_callbacks():
     prior, loglike = pc.make_callbacks(model, {p: priors.Uniform(-10, 10) for p in model.parnames})
     assert np.allclose(prior(np.array([0.5, 0.75])), [0.0, 5.0])
     assert loglike(np.array([1.0, 1.0])) == (-1.0, [])
+
+
+def test_polychord_sorted_priors_are_applied_per_group():
+    from evidence_b200 import polychord as pc
+    model = GaussianModel(3)
+    shared = priors.make_prior("SortedUniform", 1.0, 100.0)  # one object for the whole group
+    pd_ = {model.parnames[0]: shared, model.parnames[1]: priors.Uniform(0, 1), model.parnames[2]: shared}
+    prior, _ = pc.make_callbacks(model, pd_)
+    th = prior(np.array([0.3, 0.25, 0.81]))
+    assert th[1] == 0.25 and 1.0 <= th[0] <= th[2] <= 100.0  # sorted within the group
+    assert th[2] == pytest.approx(1.0 + 99.0 * 0.9) and th[0] == pytest.approx(1.0 + 99.0 * 0.3 * 0.9)
