@@ -132,6 +132,9 @@ __device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7
 constexpr int kHiTrigMax = 0x40F86A00;  // 1e5 = 0x40F86A0000000000: |x| < 1e5  <=>  abs_hi < this
 constexpr int kHiTiny = 0x3F500000;     // abs_hi(d) <  this  <=>  |d| <  2^-10
 constexpr int kHiSmall = 0x3FA00000;    // abs_hi(d) <  this  <=>  |d| <  2^-5
+#ifndef RVL_MEDIUM
+#define RVL_MEDIUM 1
+#endif
 constexpr int kHiMedium = 0x3FE80000;   // abs_hi(d) <  this  <=>  |d| <  0.75
 
 template <int U>
@@ -177,18 +180,23 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
     // libdevice, which is valid for any argument
     const bool slow = __any_sync(kFull, big || !(ec >= -0.99));
     int trip = 0;  // warp-uniform number of Newton steps taken so far
+    const int tol_hi = __double2hiint(tol);
+#pragma unroll 2
     for (;;) {
-        // (1) bring (sin E, cos E) up to date with the step d just taken
+        // warp-wide maximum of the high words of |d|: ONE redux decides the sin/cos path and
+        // (except in a 1e-6-wide band around tol) the loop exit, all on uniform values
         int hmax = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) hmax = max(hmax, abs_hi(d[u]));
-        if (VARIANT == 0 && __all_sync(kFull, hmax < kHiTiny)) {
+        const int wmax = (int)__reduce_max_sync(kFull, (unsigned)hmax);
+        // (1) bring (sin E, cos E) up to date with the step d just taken
+        if (VARIANT == 0 && wmax < kHiTiny) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_tiny(d[u], s[u], c[u]);
-        } else if (VARIANT == 0 && __all_sync(kFull, hmax < kHiSmall)) {
+        } else if (VARIANT == 0 && wmax < kHiSmall) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_small(d[u], s[u], c[u]);
-        } else if (VARIANT == 0 && !slow && __all_sync(kFull, hmax < kHiMedium)) {
+        } else if (VARIANT == 0 && RVL_MEDIUM && !slow && wmax < kHiMedium) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_medium(d[u], s[u], c[u]);
         } else if (slow || (trip > 2 && any_big<U>(E))) {
@@ -204,13 +212,16 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
             for (int u = 0; u < U; ++u) rvl::sincos_fast(E[u], s[u], c[u]);
         }
         // (2) which lanes still iterate (trueanomaly.c:21); the cap (:32-33) bounds the loop
-        bool pa[U], any_left = false;
+        bool pa[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            pa[u] = fabs(d[u]) > tol;
-            any_left = any_left || pa[u];
+        for (int u = 0; u < U; ++u) pa[u] = fabs(d[u]) > tol;
+        if (trip >= itmax || wmax < tol_hi) break;  // high word below tol's: every |d| < tol
+        if (wmax == tol_hi) {                       // rare tie on the high word: exact vote
+            bool any_left = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) any_left = any_left || pa[u];
+            if (!__any_sync(kFull, any_left)) break;
         }
-        if (trip >= itmax || !__any_sync(kFull, any_left)) break;
         ++trip;
         // (3) one Newton step for the active lanes; a frozen lane's step is exactly 0
 #pragma unroll
