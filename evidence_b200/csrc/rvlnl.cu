@@ -5,9 +5,9 @@
 //   evidence/rvmodel/__init__.py:157-219  RVModel.log_likelihood      -> rv_lnl_kernel
 //   evidence/rvmodel/__init__.py:343-463  kep_rv / modelk             -> point_setup + solve_planet
 //   evidence/rvmodel/trueanomaly.c:8-41   trueanomaly()               -> solve_planet / trueanomaly_kernel
-//   evidence/rvmodel/__init__.py:222-273  drift                       -> epoch_term
-//   evidence/rvmodel/__init__.py:59-80    BaseModel.logL              -> epoch_term + slice reduce
-//   evidence/ultranest/__init__.py:125-137 prior(hypercube)           -> prior_transform_kernel
+//   evidence/rvmodel/__init__.py:222-273  drift                       -> epoch term of rv_lnl_kernel
+//   evidence/rvmodel/__init__.py:59-80    BaseModel.logL              -> epoch term + slice reduce
+//   evidence/ultranest/__init__.py:125-137 prior(hypercube)           -> prior_transform_kernel / point_prepare_kernel
 //
 // Layout.  Epoch data lives in HBM as columns [ncol][Npad] of doubles (t, vrad, svrad^2, then
 // (t-tref)/365.25 when the model has a drift, then the linear-parameter columns) followed by
@@ -17,8 +17,9 @@
 // vectors from a per-slice work counter.  warp <-> one parameter vector, lanes <-> 32 epochs:
 // all lanes of a warp share the eccentricity, so Newton iteration counts are nearly uniform and
 // the loop exit / sin-cos path choice are warp votes.  chi^2 and log-det partial sums are
-// reduced with warp shuffles; with S > 1 the per-slice partials are combined by a tiny second
-// kernel in a fixed order (deterministic).
+// reduced with warp shuffles; with S > 1 a one-warp-per-point prepare pass computes the per-point
+// constants once (optionally fused with the prior transform), every slice writes its partial sums
+// and a small second kernel adds them in slice order (deterministic).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -45,7 +46,8 @@ struct KArgs {
     const double *theta;          // [B][ndim]
     double *lnl;                  // [B]        (written directly when S == 1)
     double *partial;              // [B][S][2]  (S > 1)
-    int *flags;                   // [B] 1 = invalid Keplerian (S > 1)
+    int *flags;                   // [B] 1 = invalid Keplerian (S > 1, or written by the prepare pass)
+    const double *consts;         // [B][wstride] per-point constants from point_prepare_kernel, or NULL
     unsigned long long *counters; // 0 newton iters, 1 cap hits, 2 invalid points
     unsigned int *work;           // [S] dynamic work counters
     long long B;
@@ -102,7 +104,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 
 __device__ __forceinline__ double par_of(const rvl_param &p, const double *row)
 {
-    return p.slot >= 0 ? __ldg(row + p.slot) : p.value;
+    return p.slot >= 0 ? row[p.slot] : p.value;
 }
 
 // shared-memory loads through a 32-bit shared-window address (one live register per base
@@ -382,16 +384,27 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
 
     unsigned long long tot_iters = 0, tot_caps = 0, tot_invalid = 0;
 
-    while (true) {
-        unsigned idx = 0;
-        if (lane == 0) idx = atomicAdd(&a.work[sl], 1u);
-        idx = __shfl_sync(kFull, idx, 0);
-        if ((long long)idx >= a.B) break;
+    // work queue of this slice: the index of the NEXT item is requested while the current one is
+    // computed, so the atomic's round trip (~1 us) is off the critical path
+    unsigned idx = 0;
+    if (lane == 0) idx = atomicAdd(&a.work[sl], 1u);
+    idx = __shfl_sync(kFull, idx, 0);
+    while ((long long)idx < a.B) {
         const long long pt = idx;
         const double *row = a.theta + pt * m.ndim;
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(&a.work[sl], 1u);
 
         __syncwarp();
-        const bool valid = point_setup(m, row, wc, lane);
+        bool valid;
+        if (a.consts) {  // constants were prepared once per point (S > 1 / fused transform)
+            const double *src = a.consts + (size_t)pt * a.wstride;
+            for (int i = lane; i < a.wstride; i += 32) wc[i] = __ldg(src + i);
+            valid = __ldg(a.flags + pt) == 0;
+            __syncwarp();
+        } else {
+            valid = point_setup(m, row, wc, lane);
+        }
 
         double chi = 0.0, prod = 1.0;
         int esum = 0, iters = 0, caps = 0;
@@ -526,12 +539,13 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
                 // (cte - sum ln sqrt var) - sum r^2/(2 var)   (:80); invalid -> -1e30 (:203)
                 a.lnl[pt] = valid ? rvl::sub(rvl::sub(a.cte, S1), S2) : -1e30;
             } else {
+                // this slice's partial sums; combine_slices_kernel adds them in slice order
                 double *o = a.partial + ((size_t)pt * a.S + sl) * 2;
                 o[0] = S1;
                 o[1] = S2;
-                if (sl == 0) a.flags[pt] = valid ? 0 : 1;
             }
         }
+        idx = __shfl_sync(kFull, next, 0);
     }
     if (lane == 0) {
         if (tot_iters) atomicAdd(&a.counters[0], tot_iters);
@@ -540,7 +554,37 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     }
 }
 
-// combine the per-slice partial sums in slice order (deterministic)
+// ---- once-per-point pass: (optional) unit cube -> theta, then the per-point constants ----------
+// One warp per point.  With U != NULL this is the fused prior transform: lane i < ndim evaluates
+// ppf_i(u_i), theta is written out (the sampler stores it) and the constants are derived from
+// exactly those values.  Used whenever the epoch axis is cut into S > 1 slices (the constants are
+// then computed once per point instead of once per slice) and for rvl_transform_loglike.
+__device__ double ppf_eval(const rvl_prior_desc &pr, const double *tables, double q);
+
+__global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc *model,
+                                                            const rvl_prior_desc *priors,
+                                                            const double *tables, const double *U,
+                                                            double *theta, double *consts,
+                                                            int *flags,
+                                                            unsigned int *work, int n_work,
+                                                            long long B, int wstride)
+{
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x < n_work) work[threadIdx.x] = 0u;  // per-slice work queues
+    const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= B) return;  // whole warps
+    const rvl_model_desc &m = *model;
+    double *row = theta + pt * m.ndim;
+    if (U) {
+        for (int i = lane; i < m.ndim; i += 32) row[i] = ppf_eval(priors[i], tables, U[pt * m.ndim + i]);
+        __syncwarp();
+    }
+    const bool valid = point_setup(m, row, consts + (size_t)pt * wstride, lane);
+    if (lane == 0) flags[pt] = valid ? 0 : 1;
+}
+
+// combine the per-slice partial sums in slice order (deterministic):
+// lnL = (cte - sum_s S1) - sum_s S2  (:80); invalid Keplerian -> -1e30 (:203)
 __global__ void combine_slices_kernel(const double *partial, const int *flags, double *lnl,
                                       long long B, int S, double cte)
 {
@@ -560,8 +604,7 @@ __global__ void combine_slices_kernel(const double *partial, const int *flags, d
 }
 
 // ---- prior transform: unit cube -> theta (evidence/ultranest/__init__.py:125-137) -----------
-__device__ __forceinline__ double ppf_eval(const rvl_prior_desc &pr, const double *tables,
-                                           double q)
+__device__ double ppf_eval(const rvl_prior_desc &pr, const double *tables, double q)
 {
     const double p0 = pr.p[0], p1 = pr.p[1];
     switch (pr.kind) {
@@ -722,12 +765,14 @@ struct rvl_handle {
     long long cap_B = 0, cap_flags = 0;
     size_t cap_partial = 0;
     double *d_theta = nullptr, *d_u = nullptr, *d_lnl = nullptr, *d_partial = nullptr;
+    double *d_consts = nullptr;
+    size_t cap_consts = 0;
     int *d_flags = nullptr;
     unsigned long long *d_counters = nullptr;  // 3
     unsigned int *d_work = nullptr;            // sm_count
 
     // options
-    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1, opt_ilp = 2;
+    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1, opt_ilp = 2, opt_min_chunks = 8, opt_items_per_warp = 4;
 
     // bookkeeping
     uint64_t n_points = 0, n_solves = 0, launches = 0;
@@ -805,18 +850,30 @@ int ensure_io(rvl_t *h, long long B)
     return RVL_OK;
 }
 
-// per-slice partial sums (only when the epoch axis is cut into S > 1 slices)
-int ensure_partial(rvl_t *h, long long B, int S)
+// per-slice partial sums (S > 1), invalid-point flags and prepared per-point constants
+int ensure_partial(rvl_t *h, long long B, int S, bool prepare, int wstride)
 {
-    if (S <= 1) return RVL_OK;
+    if (S <= 1 && !prepare) return RVL_OK;
+    if (B > h->cap_flags) {
+        cudaFree(h->d_flags);
+        h->d_flags = nullptr; h->cap_flags = 0;
+        CU(h, cudaMalloc(&h->d_flags, (size_t)B * sizeof(int)));
+        h->cap_flags = B;
+    }
     const size_t need = (size_t)B * S;
-    if (need <= h->cap_partial && B <= h->cap_flags) return RVL_OK;
-    cudaFree(h->d_partial); cudaFree(h->d_flags);
-    h->d_partial = nullptr; h->d_flags = nullptr;
-    h->cap_partial = 0; h->cap_flags = 0;
-    CU(h, cudaMalloc(&h->d_partial, need * 2 * sizeof(double)));
-    CU(h, cudaMalloc(&h->d_flags, (size_t)B * sizeof(int)));
-    h->cap_partial = need; h->cap_flags = B;
+    if (S > 1 && need > h->cap_partial) {
+        cudaFree(h->d_partial);
+        h->d_partial = nullptr; h->cap_partial = 0;
+        CU(h, cudaMalloc(&h->d_partial, need * 2 * sizeof(double)));
+        h->cap_partial = need;
+    }
+    const size_t needc = (size_t)B * wstride;
+    if (prepare && needc > h->cap_consts) {
+        cudaFree(h->d_consts);
+        h->d_consts = nullptr; h->cap_consts = 0;
+        CU(h, cudaMalloc(&h->d_consts, needc * sizeof(double)));
+        h->cap_consts = needc;
+    }
     return RVL_OK;
 }
 
@@ -854,8 +911,8 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
         // small batches: cut epochs finer so that every warp of the chip gets >= ~4 work items,
         // but keep >= 8 chunks per slice so the per-point setup stays amortised
         const long long warps_total = (long long)h->sm_count * W;
-        long long want = (4 * warps_total + B - 1) / std::max<long long>(B, 1);
-        const int maxS = std::max(1, Ctot / 8);
+        long long want = ((long long)h->opt_items_per_warp * warps_total + B - 1) / std::max<long long>(B, 1);
+        const int maxS = std::max(1, Ctot / h->opt_min_chunks);
         S = std::max<long long>(S, std::min<long long>(want, maxS));
     }
     S = std::min(S, h->sm_count);
@@ -878,25 +935,40 @@ int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
     return RVL_OK;
 }
 
-// enqueue: zero work counters, likelihood kernel, (combine).  dTheta/dlnL are device pointers.
-int enqueue_loglike(rvl_t *h, const double *dTheta, long long B, double *dlnL, cudaStream_t st,
-                    bool timed)
+// enqueue: [prepare pass], zero work counters, likelihood kernel, [combine].  All pointers are
+// device pointers.  dU != NULL: fused prior transform -- theta is WRITTEN to dTheta by the prepare
+// pass and the likelihood is evaluated on exactly those values.
+int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, double *dlnL,
+                    cudaStream_t st, bool timed)
 {
     if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
+    if (dU && !h->have_priors) return fail(h, RVL_ESTATE, "set priors first");
+    if (dU && h->prior_ndim != h->model.ndim) return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
     if (h->cols_dirty) { int rc = upload_columns(h); if (rc) return rc; }
     if (B <= 0) return RVL_OK;
     if (B > 0xfffffff0LL) return fail(h, RVL_EINVAL, "batch too large for one call (max ~4.29e9)");
     Plan pl;
     int rc = make_plan(h, B, pl);
     if (rc) return rc;
-    rc = ensure_partial(h, B, pl.S);
+    const bool prepare = pl.S > 1 || dU != nullptr;
+    rc = ensure_partial(h, B, pl.S, prepare, pl.wstride);
     if (rc) return rc;
+    if (prepare) {
+        const int wpb = 8;  // warps (= points) per block
+        point_prepare_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+            h->d_model, h->d_priors, h->d_tables, dU, dTheta, h->d_consts, h->d_flags,
+            h->d_work, h->sm_count, B, pl.wstride);
+        CU(h, cudaGetLastError());
+        ++h->launches;
+    } else {
+        CU(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned) * (size_t)h->sm_count, st));
+    }
     KArgs a{};
     a.model = h->d_model; a.cols = h->d_cols; a.inst = h->d_inst; a.theta = dTheta; a.lnl = dlnL;
     a.partial = h->d_partial; a.flags = h->d_flags; a.counters = h->d_counters; a.work = h->d_work;
+    a.consts = prepare ? h->d_consts : nullptr;
     a.B = B; a.cte = -0.5 * h->N * log(2 * M_PI); a.N = h->N; a.Npad = h->Npad; a.ncol = h->ncol;
     a.S = pl.S; a.cps = pl.cps; a.wstride = pl.wstride;
-    CU(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned) * (size_t)h->sm_count, st));
     if (timed) CU(h, cudaEventRecord(h->ev0, st));
     if (h->opt_variant == 1) rc = launch_lnl_v<1, 1, 1024>(h, a, pl, st);
     else if (pl.U == 2 && pl.W <= 16) rc = launch_lnl_v<0, 2, 512>(h, a, pl, st);
@@ -998,6 +1070,7 @@ void rvl_destroy(rvl_t *h)
     cudaFree(h->d_cols); cudaFree(h->d_inst); cudaFree(h->d_model); cudaFree(h->d_priors);
     cudaFree(h->d_tables); cudaFree(h->d_theta); cudaFree(h->d_u); cudaFree(h->d_lnl);
     cudaFree(h->d_partial); cudaFree(h->d_flags); cudaFree(h->d_counters); cudaFree(h->d_work);
+    cudaFree(h->d_consts);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1108,6 +1181,8 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
     else if (n == "slices") h->opt_slices = (int)std::max<int64_t>(0, value);
     else if (n == "warps") h->opt_warps = (int)std::max<int64_t>(0, std::min<int64_t>(32, value));
     else if (n == "timing") h->opt_timing = value != 0;
+    else if (n == "min_chunks") h->opt_min_chunks = (int)std::max<int64_t>(1, value);
+    else if (n == "items_per_warp") h->opt_items_per_warp = (int)std::max<int64_t>(1, value);
     else if (n == "ilp") { if (value != 1 && value != 2) return fail(h, RVL_EINVAL, "ilp in {1,2}"); h->opt_ilp = (int)value; }
     else return fail(h, RVL_EINVAL, "unknown option " + n);
     return RVL_OK;
@@ -1118,7 +1193,8 @@ int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, voi
     if (!h) return RVL_EINVAL;
     if (B < 0 || (B > 0 && (!dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
     DevGuard g(h->device);
-    return enqueue_loglike(h, dTheta, B, dlnL, (cudaStream_t)stream, h->opt_timing != 0);
+    return enqueue_loglike(h, nullptr, const_cast<double *>(dTheta), B, dlnL, (cudaStream_t)stream,
+                           h->opt_timing != 0);
 }
 
 int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream)
@@ -1137,9 +1213,7 @@ int rvl_transform_loglike_dev(rvl_t *h, const double *dU, int64_t B, double *dTh
     if (h->have_model && h->have_priors && h->prior_ndim != h->model.ndim)
         return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
     DevGuard g(h->device);
-    int rc = enqueue_transform(h, dU, B, dTheta, (cudaStream_t)stream);
-    if (rc) return rc;
-    return enqueue_loglike(h, dTheta, B, dlnL, (cudaStream_t)stream, h->opt_timing != 0);
+    return enqueue_loglike(h, dU, dTheta, B, dlnL, (cudaStream_t)stream, h->opt_timing != 0);
 }
 
 int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
@@ -1153,7 +1227,7 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
     if (rc) return rc;
     const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
     if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
-    rc = enqueue_loglike(h, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
+    rc = enqueue_loglike(h, nullptr, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1191,9 +1265,7 @@ int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, d
     if (rc) return rc;
     const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
     CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
-    rc = enqueue_transform(h, h->d_u, B, h->d_theta, h->stream);
-    if (rc) return rc;
-    rc = enqueue_loglike(h, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
+    rc = enqueue_loglike(h, h->d_u, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
     if (rc) return rc;
     if (Theta) CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -9,10 +9,14 @@ case = synth.make_case(cfg)
 m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
 ilp = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 m.set_option("ilp", ilp)
-if len(sys.argv) > 4:
+if len(sys.argv) > 4 and "=" not in sys.argv[4]:
     m.set_option("warps", int(sys.argv[4]))
-if len(sys.argv) > 5:
+if len(sys.argv) > 5 and "=" not in sys.argv[5]:
     m.set_option("slices", int(sys.argv[5]))
+for kv in sys.argv[4:]:
+    if "=" in kv:
+        k, v = kv.split("=")
+        m.set_option(k, int(v))
 th = torch.from_numpy(case.draw_theta(B, seed=77)).cuda()
 out = torch.empty(B, dtype=torch.float64, device='cuda')
 ms = []
