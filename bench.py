@@ -178,6 +178,7 @@ class ClockSampler:
 def sweep(model_factory, case, batch, steps, torch, peak_tflops):
     """A larger parameter sweep of another BASELINE shape (extra information, N=1 only)."""
     model = model_factory(case)
+    model.set_option("timing", 1)
     theta = torch.from_numpy(case.draw_theta(batch, seed=77)).cuda()
     out = torch.empty(batch, dtype=torch.float64, device="cuda")
     for _ in range(2):
@@ -256,6 +257,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    model.set_option("timing", 1)  # CUDA events around the likelihood kernel (off by default)
     for _ in range(W):
         step()
     barrier()
@@ -281,6 +283,7 @@ def main():
     launches = model.launch_count() - launches0
     cnt = model.counters()
 
+    model.set_option("timing", 0)
     # ---- end to end: pinned host theta -> H2D -> kernel(s) -> D2H lnL, public host API ----
     th_pin = torch.from_numpy(theta_host).pin_memory()
     out_pin = torch.empty(B, dtype=torch.float64).pin_memory()

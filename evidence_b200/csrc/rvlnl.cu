@@ -574,12 +574,22 @@ __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc
     const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pt >= B) return;  // whole warps
     const rvl_model_desc &m = *model;
+    // the row is staged in shared memory with ONE coalesced read per warp: theta / U may live in
+    // pinned host memory (zero-copy host-buffer calls), where scattered 8-byte reads are costly
+    __shared__ double srow_all[8][RVL_MAX_DIM];
+    double *srow = srow_all[threadIdx.x >> 5];
     double *row = theta + pt * m.ndim;
     if (U) {
-        for (int i = lane; i < m.ndim; i += 32) row[i] = ppf_eval(priors[i], tables, U[pt * m.ndim + i]);
-        __syncwarp();
+        for (int i = lane; i < m.ndim; i += 32) {
+            const double v = ppf_eval(priors[i], tables, U[pt * m.ndim + i]);
+            srow[i] = v;
+            row[i] = v;  // theta is an output of the fused call
+        }
+    } else {
+        for (int i = lane; i < m.ndim; i += 32) srow[i] = row[i];
     }
-    const bool valid = point_setup(m, row, consts + (size_t)pt * wstride, lane);
+    __syncwarp();
+    const bool valid = point_setup(m, srow, consts + (size_t)pt * wstride, lane);
     if (lane == 0) flags[pt] = valid ? 0 : 1;
 }
 
@@ -772,7 +782,7 @@ struct rvl_handle {
     unsigned int *d_work = nullptr;            // sm_count
 
     // options
-    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 1, opt_ilp = 2, opt_min_chunks = 8, opt_items_per_warp = 4;
+    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 0, opt_zero_copy = 1, opt_ilp = 2, opt_min_chunks = 8, opt_items_per_warp = 4;
 
     // bookkeeping
     uint64_t n_points = 0, n_solves = 0, launches = 0;
@@ -1002,6 +1012,18 @@ int enqueue_transform(rvl_t *h, const double *dU, long long B, double *dTheta, c
     return RVL_OK;
 }
 
+// Device alias of a pinned (page-locked, mapped) host buffer, or NULL for pageable memory.
+// The kernels then read theta / write lnL in place over PCIe: no staging copy, no extra launch.
+void *pinned_alias(rvl_t *h, const void *p)
+{
+    if (!h->opt_zero_copy || !p) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost)
+        return at.devicePointer;
+    cudaGetLastError();  // pageable memory: clear the error some driver versions record
+    return nullptr;
+}
+
 int finish_timing(rvl_t *h)
 {
     if (h->timing_pending) {
@@ -1181,6 +1203,7 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
     else if (n == "slices") h->opt_slices = (int)std::max<int64_t>(0, value);
     else if (n == "warps") h->opt_warps = (int)std::max<int64_t>(0, std::min<int64_t>(32, value));
     else if (n == "timing") h->opt_timing = value != 0;
+    else if (n == "zero_copy") h->opt_zero_copy = value != 0;
     else if (n == "min_chunks") h->opt_min_chunks = (int)std::max<int64_t>(1, value);
     else if (n == "items_per_warp") h->opt_items_per_warp = (int)std::max<int64_t>(1, value);
     else if (n == "ilp") { if (value != 1 && value != 2) return fail(h, RVL_EINVAL, "ilp in {1,2}"); h->opt_ilp = (int)value; }
@@ -1225,11 +1248,23 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
     DevGuard g(h->device);
     int rc = ensure_io(h, B);
     if (rc) return rc;
-    const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
-    if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
-    rc = enqueue_loglike(h, nullptr, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
+    // Pinned caller buffers are used in place (zero-copy) when the once-per-point prepare pass
+    // reads theta (one coalesced read per row); otherwise theta is staged with a copy.
+    Plan pl;
+    rc = make_plan(h, B, pl);
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
+    double *th_dev = pl.S > 1 ? (double *)pinned_alias(h, Theta) : nullptr;
+    double *out_dev = (double *)pinned_alias(h, lnL);
+    if (!th_dev) {
+        th_dev = h->d_theta;
+        if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = enqueue_loglike(h, nullptr, th_dev, B, out_dev ? out_dev : h->d_lnl, h->stream,
+                         h->opt_timing != 0);
+    if (rc) return rc;
+    if (!out_dev)
+        CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return finish_timing(h);
 }
@@ -1264,11 +1299,21 @@ int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, d
     int rc = ensure_io(h, B);
     if (rc) return rc;
     const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
-    CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
-    rc = enqueue_loglike(h, h->d_u, h->d_theta, B, h->d_lnl, h->stream, h->opt_timing != 0);
+    // pinned caller buffers are read / written in place by the prepare pass and the kernels
+    const double *u_dev = (const double *)pinned_alias(h, U);
+    double *th_dev = Theta ? (double *)pinned_alias(h, Theta) : nullptr;
+    double *out_dev = (double *)pinned_alias(h, lnL);
+    if (!u_dev) {
+        CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
+        u_dev = h->d_u;
+    }
+    rc = enqueue_loglike(h, u_dev, th_dev ? th_dev : h->d_theta, B, out_dev ? out_dev : h->d_lnl,
+                         h->stream, h->opt_timing != 0);
     if (rc) return rc;
-    if (Theta) CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Theta && !th_dev)
+        CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (!out_dev)
+        CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return finish_timing(h);
 }

@@ -153,7 +153,13 @@ int rvl_set_linpar(rvl_t *h, int32_t idx, const double *col, int32_t n);
 int rvl_set_model(rvl_t *h, const rvl_model_desc *desc);
 int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const double *tables,
                    int64_t n_table_doubles);
-/* tuning knobs, by name ("variant", "slices", "warps", ...); unknown name -> RVL_EINVAL */
+/* knobs, by name; unknown name -> RVL_EINVAL:
+ *   "timing"    1: record CUDA events around the likelihood kernel (rvl_last_kernel_ms); default 0
+ *   "zero_copy" 1 (default): host-buffer calls whose buffers are page-locked (pinned) are served in
+ *               place -- the kernels read theta/U and write theta/lnL over PCIe, no staging copies
+ *   "variant"   0 optimised kernel (default), 1 conservative cross-check (IEEE division, full sin/cos)
+ *   "ilp"       epochs per lane in flight, 1 or 2 (default 2)
+ *   "slices", "warps", "min_chunks", "items_per_warp": launch-plan overrides (0 = automatic) */
 int rvl_set_option(rvl_t *h, const char *name, int64_t value);
 
 /* ---- hot path: host buffers, synchronous -------------------------------- */

@@ -320,3 +320,44 @@ def test_degenerate_variance_falls_back_to_plain_logs():
     for g, w in ((got[0], want[0]), (got[2], want[2])):
         assert (np.isnan(g) and np.isnan(w)) or g == w or (not np.isfinite(g) and not np.isfinite(w))
     m.close()
+
+
+def test_pinned_host_buffers_are_served_in_place(models):
+    """Zero-copy path (pinned theta / lnL) gives the same bits as the staged path."""
+    import torch
+    meta, z, m = models("cfg2")
+    theta = z["theta"]
+    staged = m.log_likelihood_batch(theta)  # pageable numpy -> staging copies
+    th_pin = torch.from_numpy(theta).pin_memory()
+    out_pin = torch.empty(len(theta), dtype=torch.float64).pin_memory()
+    m.log_likelihood_batch(th_pin.numpy(), out=out_pin.numpy())
+    assert np.array_equal(out_pin.numpy(), staged)
+    m.set_option("zero_copy", 0)
+    m.log_likelihood_batch(th_pin.numpy(), out=out_pin.numpy())
+    m.set_option("zero_copy", 1)
+    assert np.array_equal(out_pin.numpy(), staged)
+    # fused transform + likelihood with pinned U / theta / lnL
+    from evidence_b200 import synth
+    case = synth.make_case(2)
+    m2 = device_model(meta, z)
+    m2.set_priors(case.priordict)
+    U = case.draw_unit(300, seed=4)
+    th_a, l_a = m2.transform_loglike_batch(U)
+    u_pin = torch.from_numpy(U).pin_memory()
+    th_pin2 = torch.empty_like(u_pin).pin_memory()
+    l_pin = torch.empty(300, dtype=torch.float64).pin_memory()
+    from ctypes import POINTER, c_double
+    dp = POINTER(c_double)
+    rc = m2._lib.rvl_transform_loglike(m2._h, u_pin.numpy().ctypes.data_as(dp), 300,
+                                       th_pin2.numpy().ctypes.data_as(dp), l_pin.numpy().ctypes.data_as(dp))
+    assert rc == 0
+    assert np.array_equal(th_pin2.numpy(), th_a) and np.array_equal(l_pin.numpy(), l_a)
+    m2.close()
+
+
+def test_kernel_timing_is_opt_in(models):
+    meta, z, m = models("cfg1")
+    m.set_option("timing", 1)
+    m.log_likelihood_batch(z["theta"])
+    assert 0.0 < m.last_kernel_ms() < 50.0
+    m.set_option("timing", 0)

@@ -7,7 +7,8 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 case = synth.make_case(cfg)
 m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
-ilp = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+m.set_option("timing", 1)
+ilp = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 m.set_option("ilp", ilp)
 if len(sys.argv) > 4 and "=" not in sys.argv[4]:
     m.set_option("warps", int(sys.argv[4]))
