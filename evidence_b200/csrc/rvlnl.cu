@@ -905,8 +905,8 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     int wstride = m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar;
     wstride = (wstride + 1) & ~1;
     const int U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
-    int W = h->opt_warps > 0 ? h->opt_warps : (U == 2 ? 24 : 32);
-    W = std::max(1, std::min(U == 2 ? 24 : 32, W));
+    int W = h->opt_warps > 0 ? h->opt_warps : (U == 2 ? 28 : 32);
+    W = std::max(1, std::min(32, W));
     // smallest slice count whose slice fits in shared memory
     int S = 1;
     auto fits = [&](int s) {
@@ -982,7 +982,10 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     if (timed) CU(h, cudaEventRecord(h->ev0, st));
     if (h->opt_variant == 1) rc = launch_lnl_v<1, 1, 1024>(h, a, pl, st);
     else if (pl.U == 2 && pl.W <= 16) rc = launch_lnl_v<0, 2, 512>(h, a, pl, st);
-    else if (pl.U == 2) rc = launch_lnl_v<0, 2, 768>(h, a, pl, st);
+    else if (pl.U == 2 && pl.W <= 20) rc = launch_lnl_v<0, 2, 640>(h, a, pl, st);
+    else if (pl.U == 2 && pl.W <= 24) rc = launch_lnl_v<0, 2, 768>(h, a, pl, st);
+    else if (pl.U == 2 && pl.W <= 28) rc = launch_lnl_v<0, 2, 896>(h, a, pl, st);
+    else if (pl.U == 2) rc = launch_lnl_v<0, 2, 1024>(h, a, pl, st);
     else rc = launch_lnl_v<0, 1, 1024>(h, a, pl, st);
     if (rc) return rc;
     if (timed) { CU(h, cudaEventRecord(h->ev1, st)); h->timing_pending = true; }
