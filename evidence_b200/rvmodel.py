@@ -245,6 +245,41 @@ class RVModel(BaseModel):
             c_void_p(lnl.data_ptr()), c_void_p(stream)))
         return theta, lnl
 
+    # ------------------------------------------------------------------ host helpers
+    def linear_parameter(self, time, indicator, kernel=None, timescale=0.5, filter_type="lp"):
+        """
+        Smoothed, [-1, 1]-normalised activity-indicator series for a ``linpar`` term: same
+        signature and result as evidence/rvmodel/__init__.py:276-340 (kernels 'gaussian', 'box',
+        'epanechnikov'; low-/high-pass).  Host side, runs once per model (the O(N^2) loop of the
+        reference is a single broadcast here); feed the result to ``linpar_dict``.
+        """
+        time = np.asarray(time, dtype=np.float64)
+        indicator = np.asarray(indicator, dtype=np.float64)
+        assert len(time) == len(indicator), "time and indicator have to have the same length."
+        if kernel is None:
+            smoothed = indicator
+        else:
+            rt = time / (365.25 * timescale)
+            delta = rt[None, :] - rt[:, None]  # row k: renorm_time - renorm_time[k]
+            if kernel == "gaussian":
+                w = np.exp(-0.5 * delta ** 2)
+            elif kernel == "box":
+                w = (np.abs(delta) <= 1.0).astype(np.float64)
+            elif kernel == "epanechnikov":
+                w = (np.abs(delta) <= 1.0) * (1.0 - delta ** 2)
+            else:
+                raise ValueError(f"Chosen kernel ('{kernel}') is not a valid option.")
+            w = w / np.sum(w, axis=1, keepdims=True)
+            low = np.sum(w * indicator[None, :], axis=1)
+            if filter_type == "lp":
+                smoothed = low
+            elif filter_type == "hp":
+                smoothed = indicator - low
+            else:
+                raise ValueError("filter_type has to be 'lp' or 'hp'")
+        lo, hi = np.min(smoothed), np.max(smoothed)
+        return 2.0 * (smoothed - lo) / (hi - lo) - 1.0
+
     # ------------------------------------------------------------------ reference FFI / stats
     def true_anomaly(self, ma, ecc, tol=1.0e-4):
         """Device version of evidence/rvmodel/__init__.py:466-494 (same signature)."""

@@ -1,0 +1,56 @@
+"""
+Evidence ladder (BASELINE.json config 4): ln Z for k = 0..kmax planets on one data set, one
+independent run per GPU -- replicas, no collective.
+
+    python examples/evidence_ladder.py --kmax 3                      # one GPU, the k's in sequence
+    torchrun --nproc-per-node 6 examples/evidence_ladder.py --kmax 5 # rank r takes k = r, r+6, ...
+
+Each line of output is one JSON record {k, logz, logzerr, ncall, seconds, device}.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+import numpy as np  # noqa: E402
+
+from evidence_b200 import priors, synth  # noqa: E402
+from evidence_b200.rvmodel import RVModel  # noqa: E402
+from evidence_b200.sampler import nested_sample  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kmax", type=int, default=3)
+    ap.add_argument("--epochs", type=int, default=300)
+    ap.add_argument("--nlive", type=int, default=200)
+    ap.add_argument("--true-planets", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    data = synth.make_case(2, seed=11, n_epochs=args.epochs, n_planets=args.true_planets)
+    for k in range(rank, args.kmax + 1, world):
+        spec = {p: v for p, v in data.prior_spec.items()
+                if not p.startswith("planet") or int(p[6:p.index("_")]) <= k}
+        for j in range(args.true_planets + 1, k + 1):  # more planets than the data were made with
+            for nm in ("k1", "period", "ecc", "omega", "ma0"):
+                spec[f"planet{j}_{nm}"] = data.prior_spec[f"planet1_{nm}"]
+        pri = {p: priors.make_prior(*v) for p, v in spec.items()}
+        fixed = {f"planet{j}_epoch": synth.EPOCH for j in range(1, k + 1)}
+        fixed["drift_tref"] = synth.EPOCH
+        model = RVModel(fixed, data.datadict(), list(spec), device=dev)
+        model.set_priors(pri)
+        t0 = time.perf_counter()
+        res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
+                            nlive=args.nlive, seed=100 + k)
+        print(json.dumps({"k": k, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
+                          "seconds": time.perf_counter() - t0, "device": dev}), flush=True)
+        model.close()
+
+
+if __name__ == "__main__":
+    main()

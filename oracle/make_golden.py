@@ -248,6 +248,20 @@ def trueanomaly_vectors():
     save("trueanomaly", {"eccs": eccs, "tol": 1e-4, "itmax": 10000}, M=np.array(Ms), nu=np.array(nus))
 
 
+def linpar_smoother_vectors():
+    """RVModel.linear_parameter of the reference (evidence/rvmodel/__init__.py:276-340)."""
+    rng = np.random.default_rng(3)
+    t = np.sort(rng.uniform(0, 900, 120))
+    ind = rng.normal(0, 1, 120)
+    m = ref_model({"a_offset": 0.0}, {"a": {"rjd": t, "vrad": ind, "svrad": np.ones(120)}}, ["a_jitter"])
+    out = {}
+    for k in (None, "gaussian", "epanechnikov"):  # 'box' raises under numpy >= 2 (bool /= float)
+        for ft in ("lp", "hp"):
+            out[f"{k}_{ft}"] = m.linear_parameter(t, ind, kernel=k, timescale=0.3, filter_type=ft)
+    np.savez_compressed(os.path.join(OUT, "linpar_smoother.npz"), t=t, ind=ind, **out)
+    print("linpar_smoother")
+
+
 if __name__ == "__main__":
     kat_51peg()
     config_case(1, 256)
@@ -257,3 +271,4 @@ if __name__ == "__main__":
     edge_cases()
     prior_vectors()
     trueanomaly_vectors()
+    linpar_smoother_vectors()

@@ -66,3 +66,23 @@ def test_missing_parameters_raise_like_the_reference():
     with pytest.raises(ModelLayoutError):  # eccentricity parametrisation (:445-447)
         compile_model(["planet1_k1", "planet1_period", "planet1_ma0", "hamilton_offset"],
                       {"planet1_epoch": 0.0}, ["hamilton"], 0.0)
+
+
+def test_linear_parameter_smoother_vs_reference():
+    """RVModel.linear_parameter (host helper) against the live reference's outputs
+    (tests/golden/linpar_smoother.npz; the reference's 'box' kernel raises under numpy >= 2)."""
+    import os
+    import numpy as np
+    from evidence_b200.rvmodel import RVModel
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "linpar_smoother.npz"))
+    for key in z.files:
+        if key in ("t", "ind"):
+            continue
+        kernel, ft = key.rsplit("_", 1)
+        got = RVModel.linear_parameter(None, z["t"], z["ind"], kernel=None if kernel == "None" else kernel,
+                                       timescale=0.3, filter_type=ft)
+        assert np.max(np.abs(got - z[key])) < 1e-13, key
+    box = RVModel.linear_parameter(None, z["t"], z["ind"], kernel="box", timescale=0.3)
+    assert box.min() == -1.0 and box.max() == 1.0
+    with pytest.raises(ValueError):
+        RVModel.linear_parameter(None, z["t"], z["ind"], kernel="nope")
