@@ -92,7 +92,7 @@ def cpu_rate(case, theta, cores, budget_s=12.0):
     return n / dt, n, dt, kind
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     from evidence_b200 import synth
@@ -119,7 +119,7 @@ def run_reference(args, rank, world):
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -211,6 +211,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline and sweeps")
+    ap.add_argument("--gather", default="nccl", choices=["fused", "nccl"],
+                    help="multi-GPU: NCCL all_gather (default) or the all-gather fused into the "
+                         "producing kernel over NVLink symmetric memory")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -218,8 +221,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner,
+    # torchrun notices) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -247,6 +259,14 @@ def main():
     theta = torch.from_numpy(theta_host).cuda()
     lnl = torch.empty(B, dtype=torch.float64, device="cuda")
     sharded = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk, out=lnl), case.ndim)
+    gather = "none" if world == 1 else "nccl all_gather"
+    if world > 1 and args.gather == "fused":
+        try:  # all-gather fused into the producing kernel over NVLink symmetric memory
+            from evidence_b200.multigpu import FusedGatherLikelihood
+            sharded = FusedGatherLikelihood(model, B)
+            gather = "fused into the kernel (peer stores over NVLink symmetric memory + signal barrier)"
+        except Exception as exc:  # symmetric memory unavailable: NCCL all-gather
+            print(f"fused gather unavailable ({exc!r}); using NCCL all_gather", file=sys.stderr)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
@@ -330,7 +350,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(case, B, world),
+        "config": dict(workload_config(case, B, world), gather=gather),
         "clocks": clk,
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(B * case.ndim * 8), "d2h_bytes_per_step": int(B * 8)},
@@ -370,7 +390,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": "failed: " + repr(exc)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     model.close()
     if world > 1:
         dist.destroy_process_group()

@@ -14,6 +14,7 @@ RVL_MAX_PLANETS = 8
 RVL_MAX_INST = 16
 RVL_MAX_LINPAR = 8
 RVL_MAX_DIM = 128
+RVL_MAX_PEERS = 16
 
 RVL_ECC_DIRECT, RVL_ECC_SECOS_SESIN, RVL_ECC_ECOS_ESIN = 0, 1, 2
 RVL_PHASE_MA0, RVL_PHASE_ML0 = 0, 1
@@ -74,6 +75,8 @@ SYMBOLS = {
     "rvl_transform_loglike": (c_int32, [c_void_p, _dp, c_int64, _dp, _dp]),
     "rvl_transform_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "rvl_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "rvl_loglike_dev_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),
+                                          c_int32, c_int64, c_void_p]),
     "rvl_transform_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                             c_void_p]),
     "rvl_trueanomaly": (c_int32, [c_void_p, _dp, c_int32, c_double, _dp, c_int32, c_double]),

@@ -593,24 +593,44 @@ __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc
     if (lane == 0) flags[pt] = valid ? 0 : 1;
 }
 
+// Peer buffers of the fused all-gather: device pointers into the other ranks' (and our own)
+// gathered lnL vectors (NVLink peer / symmetric memory).  Passed by value.
+struct PeerOut {
+    double *ptr[RVL_MAX_PEERS];
+    int n;
+    long long offset;  // element offset of this rank's block inside every gathered vector
+};
+
 // combine the per-slice partial sums in slice order (deterministic):
-// lnL = (cte - sum_s S1) - sum_s S2  (:80); invalid Keplerian -> -1e30 (:203)
+// lnL = (cte - sum_s S1) - sum_s S2  (:80); invalid Keplerian -> -1e30 (:203).
+// With peers: the result is also stored straight into every rank's gathered vector over
+// NVLink -- the all-gather is fused into the producing kernel.
 __global__ void combine_slices_kernel(const double *partial, const int *flags, double *lnl,
-                                      long long B, int S, double cte)
+                                      long long B, int S, double cte, const PeerOut peers)
 {
     const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= B) return;
-    if (flags[pt]) {
-        lnl[pt] = -1e30;
-        return;
+    double v = -1e30;
+    if (!flags[pt]) {
+        const double *p = partial + (size_t)pt * S * 2;
+        double s1 = 0.0, s2 = 0.0;
+        for (int s = 0; s < S; ++s) {
+            s1 = rvl::add(s1, p[2 * s]);
+            s2 = rvl::add(s2, p[2 * s + 1]);
+        }
+        v = rvl::sub(rvl::sub(cte, s1), s2);
     }
-    const double *p = partial + (size_t)pt * S * 2;
-    double s1 = 0.0, s2 = 0.0;
-    for (int s = 0; s < S; ++s) {
-        s1 = rvl::add(s1, p[2 * s]);
-        s2 = rvl::add(s2, p[2 * s + 1]);
-    }
-    lnl[pt] = rvl::sub(rvl::sub(cte, s1), s2);
+    lnl[pt] = v;
+    for (int r = 0; r < peers.n; ++r) peers.ptr[r][peers.offset + pt] = v;
+}
+
+// S == 1 (the likelihood kernel wrote lnL itself): push the finished block to the peers
+__global__ void scatter_peers_kernel(const double *lnl, long long B, const PeerOut peers)
+{
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= B) return;
+    const double v = lnl[pt];
+    for (int r = 0; r < peers.n; ++r) peers.ptr[r][peers.offset + pt] = v;
 }
 
 // ---- prior transform: unit cube -> theta (evidence/ultranest/__init__.py:125-137) -----------
@@ -949,7 +969,7 @@ int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
 // device pointers.  dU != NULL: fused prior transform -- theta is WRITTEN to dTheta by the prepare
 // pass and the likelihood is evaluated on exactly those values.
 int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, double *dlnL,
-                    cudaStream_t st, bool timed)
+                    cudaStream_t st, bool timed, const PeerOut *peers = nullptr)
 {
     if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
     if (dU && !h->have_priors) return fail(h, RVL_ESTATE, "set priors first");
@@ -992,8 +1012,14 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     ++h->launches;
     if (pl.S > 1) {
         const int tb = 256;
-        combine_slices_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(h->d_partial, h->d_flags,
-                                                                         dlnL, B, pl.S, a.cte);
+        PeerOut none{};
+        combine_slices_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(
+            h->d_partial, h->d_flags, dlnL, B, pl.S, a.cte, peers ? *peers : none);
+        CU(h, cudaGetLastError());
+        ++h->launches;
+    } else if (peers && peers->n > 0) {
+        const int tb = 256;
+        scatter_peers_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(dlnL, B, *peers);
         CU(h, cudaGetLastError());
         ++h->launches;
     }
@@ -1221,6 +1247,23 @@ int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, voi
     DevGuard g(h->device);
     return enqueue_loglike(h, nullptr, const_cast<double *>(dTheta), B, dlnL, (cudaStream_t)stream,
                            h->opt_timing != 0);
+}
+
+int rvl_loglike_dev_scatter(rvl_t *h, const double *dTheta, int64_t B, double *dlnL,
+                            const uint64_t *peer_ptrs, int32_t n_peers, int64_t offset,
+                            void *stream)
+{
+    if (!h) return RVL_EINVAL;
+    if (B < 0 || (B > 0 && (!dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (n_peers < 0 || n_peers > RVL_MAX_PEERS || (n_peers > 0 && !peer_ptrs) || offset < 0)
+        return fail(h, RVL_EINVAL, "bad peer list");
+    PeerOut po{};
+    po.n = n_peers;
+    po.offset = offset;
+    for (int r = 0; r < n_peers; ++r) po.ptr[r] = reinterpret_cast<double *>(peer_ptrs[r]);
+    DevGuard g(h->device);
+    return enqueue_loglike(h, nullptr, const_cast<double *>(dTheta), B, dlnL, (cudaStream_t)stream,
+                           h->opt_timing != 0, &po);
 }
 
 int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream)

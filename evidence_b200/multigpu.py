@@ -7,6 +7,15 @@ The path has no other exchange step: every parameter vector's lnL depends only o
 on the small, replicated epoch data.  Rank r owns rows
 ``[r*ceil(B/R), min(B, (r+1)*ceil(B/R)))``; the tail is padded so that the collective has equal
 counts on every rank.
+
+Two ways to do the gather:
+
+* ``ShardedLikelihood`` -- the likelihood kernel, then ``all_gather_into_tensor`` (NCCL).
+* ``FusedGatherLikelihood`` -- the all-gather is fused into the producing kernel: the kernel that
+  finishes lnL stores each value straight into every rank's gathered vector through NVLink
+  peer-mapped (symmetric) memory (``rvl_loglike_dev_scatter``), and the ranks then meet at one
+  signal barrier.  No collective launch, no staging copy; saves the latency of a separate
+  all-gather on these 4 KB - 10 MB messages.
 """
 import math
 
@@ -69,3 +78,44 @@ def split_rows(theta, world_size):
     theta = np.asarray(theta)
     B = theta.shape[0]
     return [theta[slice(*shard_bounds(B, world_size, r)[:2])] for r in range(world_size)]
+
+
+class FusedGatherLikelihood:
+    """
+    Weak-scaling evaluator whose all-gather is fused into the likelihood kernel (see the module
+    docstring).  Every rank calls ``evaluate_local(theta_block)`` with its own block of the same
+    row count and receives the gathered ``lnL[world * rows]`` (a view into symmetric memory that
+    stays valid until the call after next: two buffers alternate).
+    """
+
+    def __init__(self, model, max_rows, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.model = model
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.max_rows = int(max_rows)
+        grp = group if group is not None else dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.bufs, self.hdls, self.ptrs = [], [], []
+        for _ in range(2):
+            buf = symm.empty(self.world * self.max_rows, dtype=torch.float64, device=dev)
+            hdl = symm.rendezvous(buf, grp)
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.ptrs.append([int(p) for p in hdl.buffer_ptrs])
+        self.local = torch.empty(self.max_rows, dtype=torch.float64, device=dev)
+        self.turn = 0
+
+    def evaluate_local(self, theta_block):
+        rows = theta_block.shape[0]
+        if rows > self.max_rows:
+            raise ValueError("block larger than the symmetric buffer")
+        k = self.turn
+        self.turn ^= 1
+        # every lnL value is written into all ranks' buffer k at [rank*rows + i] by the kernel
+        self.model.log_likelihood_device_scatter(theta_block, self.local[:rows], self.ptrs[k],
+                                                 self.rank * rows)
+        self.hdls[k].barrier()  # all peers' stores have landed
+        return self.bufs[k][: self.world * rows]

@@ -200,6 +200,23 @@ class RVModel(BaseModel):
                                               c_void_p(out.data_ptr()), c_void_p(stream)))
         return out
 
+    def log_likelihood_device_scatter(self, theta, out, peer_ptrs, offset):
+        """
+        ``log_likelihood_device`` whose producing kernel also stores lnL into the peer-mapped
+        buffers ``peer_ptrs`` (device addresses, e.g. torch symmetric memory ``buffer_ptrs``) at
+        element ``offset``: the all-gather of the multi-GPU path without a separate collective.
+        """
+        import torch
+        if not (theta.is_cuda and theta.dtype == torch.float64 and theta.is_contiguous()):
+            raise ValueError("theta must be a contiguous CUDA float64 tensor")
+        B = theta.shape[0]
+        arr = (c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        stream = torch.cuda.current_stream(theta.device).cuda_stream
+        self._check(self._lib.rvl_loglike_dev_scatter(
+            self._h, c_void_p(theta.data_ptr()), B, c_void_p(out.data_ptr()), arr, len(peer_ptrs),
+            int(offset), c_void_p(stream)))
+        return out
+
     # ------------------------------------------------------------------ priors
     def set_priors(self, priordict):
         """

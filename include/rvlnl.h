@@ -46,6 +46,7 @@ extern "C" {
 #define RVL_MAX_INST 16
 #define RVL_MAX_LINPAR 8
 #define RVL_MAX_DIM 128
+#define RVL_MAX_PEERS 16
 
 /* error codes */
 #define RVL_OK 0
@@ -175,6 +176,16 @@ int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, voi
 int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, void *stream);
 int rvl_transform_loglike_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta,
                               double *dlnL, void *stream);
+
+/* ---- multi-GPU: the all-gather fused into the producing kernel -------------------- */
+/* Like rvl_loglike_dev, and additionally every lnL[i] is stored into n_peers peer-mapped device
+ * buffers (NVLink peer / symmetric memory of the other ranks, and our own gathered vector) at
+ * element `offset + i`, by the same kernel that produces it.  The caller synchronises the ranks
+ * afterwards (one signal barrier) instead of running a separate all-gather collective.
+ * peer_ptrs: n_peers device addresses as 64-bit integers. */
+int rvl_loglike_dev_scatter(rvl_t *h, const double *dTheta, int64_t B, double *dlnL,
+                            const uint64_t *peer_ptrs, int32_t n_peers, int64_t offset,
+                            void *stream);
 
 /* ---- the reference's own native FFI, on the device (trueanomaly.h:4) ----- */
 /* Same contract as the reference symbol except: returns -1 when ANY element hit the cap
