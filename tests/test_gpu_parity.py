@@ -361,3 +361,81 @@ def test_kernel_timing_is_opt_in(models):
     m.log_likelihood_batch(z["theta"])
     assert 0.0 < m.last_kernel_ms() < 50.0
     m.set_option("timing", 0)
+
+
+def test_random_model_structures_vs_numpy_oracle():
+    """
+    40 seeded random model structures -- every combination the name-driven rules allow: per planet
+    k1|logk1, period|logperiod, ecc/omega | secos/sesin | ecos/esin, ma0|ml0, any parameter free or
+    fixed, 0-3 planets, 1-3 instruments, jitter free / fixed / absent, drift orders 0-4 with or
+    without drift_tref -- against the numpy oracle, which resolves names like the reference does.
+    """
+    from evidence_b200.rvmodel import RVModel
+    from oracle.rv_oracle import OracleRVModel
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n_inst = int(rng.integers(1, 4))
+        K = int(rng.integers(0, 4))
+        n = int(rng.integers(3, 150))
+        insts = [f"spec{i}" for i in range(n_inst)]
+        t = np.sort(rng.uniform(2000.0, 2600.0, n))
+        cuts = np.sort(rng.choice(np.arange(1, n), n_inst - 1, replace=False)) if n_inst > 1 else []
+        parts = np.split(np.arange(n), cuts)
+
+        def tables():
+            return {nm: {"data": {"rjd": t[ix].copy(), "vrad": vr[ix].copy(), "svrad": sv[ix].copy()}}
+                    for nm, ix in zip(insts, parts)}
+        vr, sv = rng.normal(0, 7, n), rng.uniform(0.3, 3.0, n)
+        free, fixed, box = [], {}, {}
+
+        def put(name, lo, hi, must_free=False):
+            box[name] = (lo, hi)
+            if must_free or rng.random() < 0.7:
+                free.append(name)
+            else:
+                fixed[name] = float(rng.uniform(lo, hi))
+        for p in range(1, K + 1):
+            pre = f"planet{p}_"
+            # the planet only exists for the reference if its amplitude name is FREE (:122-124)
+            put(pre + ("k1" if rng.random() < 0.6 else "logk1"), 0.1, 3.0, must_free=True)
+            put(pre + ("period" if rng.random() < 0.6 else "logperiod"), 1.2, 5.0)
+            mode = rng.integers(0, 3)
+            if mode == 0:
+                put(pre + "ecc", 0.0, 0.9); put(pre + "omega", 0.0, 6.28)
+            elif mode == 1:
+                put(pre + "secos", -0.75, 0.75); put(pre + "sesin", -0.75, 0.75)
+            else:
+                put(pre + "ecos", -0.7, 0.7); put(pre + "esin", -0.7, 0.7)
+            put(pre + ("ma0" if rng.random() < 0.5 else "ml0"), 0.0, 6.28)
+            fixed[pre + "epoch"] = float(rng.uniform(2200, 2400))
+        jit = rng.integers(0, 3)  # 0 absent, 1 free somewhere, 2 all fixed (ignored by the reference)
+        for i, nm in enumerate(insts):
+            put(nm + "_offset", -4, 4)
+            if jit == 1:
+                put(nm + "_jitter", 0.1, 3.0, must_free=(i == 0))
+            elif jit == 2:
+                fixed[nm + "_jitter"] = 2.0
+        if jit == 1:  # every instrument needs its jitter once jitter is in the model (:190)
+            for nm in insts:
+                if nm + "_jitter" not in free and nm + "_jitter" not in fixed:
+                    fixed[nm + "_jitter"] = 1.0
+        order = int(rng.integers(0, 5))
+        for j, nm in enumerate(("lin", "quad", "cub", "quar")[:order]):
+            put("drift_" + nm, -0.3, 0.3, must_free=(j == 0))
+        if order and rng.random() < 0.5:
+            fixed["drift_tref"] = 2300.0
+        if not free:
+            free.append(insts[0] + "_offset"); fixed.pop(insts[0] + "_offset", None)
+            box[insts[0] + "_offset"] = (-4, 4)
+        m = RVModel(dict(fixed), tables(), list(free))
+        om = OracleRVModel(dict(fixed), tables(), list(free))
+        assert m.parnames == om.parnames and m.nplanets == om.nplanets
+        B = 24
+        theta = np.stack([rng.uniform(*box[p], B) for p in m.parnames], axis=1)
+        want = om.log_likelihood_batch(theta)
+        got = m.log_likelihood_batch(theta)
+        log_period = any("logperiod" in p for p in list(free) + list(fixed))
+        # exp(logperiod) is the one ulp-hypersensitive input (DESIGN.md section 3)
+        ok, worst = lnl_close(got, want, abs_tol=5e-8 if log_period else 1e-9)
+        assert ok, (trial, sorted(free), sorted(fixed), worst)
+        m.close()
