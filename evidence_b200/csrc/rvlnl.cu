@@ -16,7 +16,7 @@
 // 1-D TMA bulk copies (cp.async.bulk + mbarrier), then stays resident: its warps pull parameter
 // vectors from a per-slice work counter.  warp <-> one parameter vector, lanes <-> 32 epochs:
 // all lanes of a warp share the eccentricity, so Newton iteration counts are nearly uniform and
-// the loop exit / sin-cos path choice are warp votes.  chi^2 and log-det partial sums are
+// the loop exit / sin-cos path choice come from one warp redux per trip.  chi^2 and log-det sums are
 // reduced with warp shuffles; with S > 1 a one-warp-per-point prepare pass computes the per-point
 // constants once (optionally fused with the prior transform), every slice writes its partial sums
 // and a small second kernel adds them in slice order (deterministic).
@@ -571,9 +571,17 @@ __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc
 {
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x < n_work) work[threadIdx.x] = 0u;  // per-slice work queues
+    // the model description is read many times per point: one cooperative copy to shared memory
+    __shared__ __align__(16) unsigned char s_model[sizeof(rvl_model_desc)];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(model);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_model);
+        for (int i = threadIdx.x; i < (int)(sizeof(rvl_model_desc) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pt >= B) return;  // whole warps
-    const rvl_model_desc &m = *model;
+    const rvl_model_desc &m = *reinterpret_cast<const rvl_model_desc *>(s_model);
     // the row is staged in shared memory with ONE coalesced read per warp: theta / U may live in
     // pinned host memory (zero-copy host-buffer calls), where scattered 8-byte reads are costly
     __shared__ double srow_all[8][RVL_MAX_DIM];
