@@ -83,6 +83,10 @@ def cpu_rate(case, theta, cores, budget_s=12.0):
         t0 = time.perf_counter()
         pool.map(_cpu_eval, np.array_split(probe, cores))
         rate0 = len(probe) / (time.perf_counter() - t0)
+        probe2 = np.tile(theta, (-(-int(rate0) // len(theta)), 1))[: max(len(probe), int(rate0))]
+        t0 = time.perf_counter()  # longer probe: the first one is dominated by start-up costs
+        pool.map(_cpu_eval, np.array_split(probe2, cores * 4))
+        rate0 = len(probe2) / (time.perf_counter() - t0)
         n = int(max(len(probe), rate0 * budget_s))
         reps = -(-n // len(theta))
         sample = np.tile(theta, (reps, 1))[:n]  # the step's rows, repeated to fill the budget
@@ -115,6 +119,10 @@ def run_reference(args, rank, world, emit):
         t0 = time.perf_counter()
         pool.map(_cpu_eval, np.array_split(probe, cores))
         rate0 = len(probe) / (time.perf_counter() - t0)
+        probe2 = np.tile(theta, (-(-int(rate0 * 2) // len(theta)), 1))[: max(cores * 8, int(rate0 * 2))]
+        t0 = time.perf_counter()  # second, longer probe: the first is dominated by start-up costs
+        pool.map(_cpu_eval, np.array_split(probe2, cores * 4))
+        rate0 = len(probe2) / (time.perf_counter() - t0)
         n = int(max(cores * 4, rate0 * per_step_s))
         sample = np.tile(theta, (-(-n // len(theta)), 1))[:n]
         chunks = np.array_split(sample, cores * 4)
