@@ -303,7 +303,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    model.set_option("timing", 1)  # CUDA events around the likelihood kernel (off by default)
+    # At N = 1 a step IS one launch of the likelihood kernel (the work list, the per-point
+    # constants and the slice sums all live inside it), so the step's CUDA events time the kernel;
+    # with an all-gather in the step the library records its own events around the kernel.
+    inner_events = world > 1
+    model.set_option("timing", 1 if inner_events else 0)
     for _ in range(W):
         step()
     barrier()
@@ -321,12 +325,17 @@ def main():
         ev[k][0].record()
         step()
         ev[k][1].record()
-        kms.append(model.last_kernel_ms())
+        if inner_events:
+            kms.append(model.last_kernel_ms())
     barrier()
     t_wall = time.perf_counter() - t_wall
     clk = clocks.stop()
     dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     launches = model.launch_count() - launches0
+    if not inner_events:
+        if launches != K:
+            raise SystemExit(f"expected one launch per step, counted {launches} in {K} steps")
+        kms = [a.elapsed_time(b) for a, b in ev]
     cnt = model.counters()
 
     model.set_option("timing", 0)
@@ -384,6 +393,8 @@ def main():
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "kernel": "rv_lnl_kernel", "kernel_ms": k_ms,
+                     "kernel_ms_source": ("library CUDA events around the kernel" if inner_events else
+                                          "the step's CUDA events (one launch per step)"),
                      "flops_per_lnl": F, "mean_newton_iters": mean_it,
                      "peak_source": "DFMA loop measured in this run (rvl_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 row",

@@ -87,6 +87,8 @@ SYMBOLS = {
     "rvl_fp64_peak": (c_int32, [c_void_p, _dp]),
     "rvl_device_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32)]),
+    "rvl_read_trace": (c_int32, [c_void_p, POINTER(c_uint64), c_int32, POINTER(c_int32)]),
+    "rvl_plan_describe": (c_int32, [POINTER(c_int32), c_int64, POINTER(c_int64), c_int32]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librvlnl.so")

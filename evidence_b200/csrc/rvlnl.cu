@@ -39,22 +39,53 @@ constexpr int kPlanetStride = 8;  // doubles per planet in the per-warp constant
 constexpr int kModelBytes = (int)((sizeof(rvl_model_desc) + 127) / 128 * 128);
 // per-planet constants: 0 nmot, 1 M0, 2 ec, 3 A, 4 Bs, 5 Ce, 6 epoch
 
+// Peer buffers of the fused all-gather: device pointers into the other ranks' (and our own)
+// gathered lnL vectors (NVLink peer / symmetric memory).  Passed by value.
+struct PeerOut {
+    double *ptr[RVL_MAX_PEERS];
+    int n;
+    long long offset;  // element offset of this rank's block inside every gathered vector
+};
+
+// One phase of the work list of a queue.  Items idx0 .. (next phase's idx0 - 1) cover points
+// pt0, pt0+1, ... ; every point is cut into S sub-slices of cps chunks (of the block's resident
+// epoch range), one item each.  Phases run from coarse (whole points) to fine (a pair of chunks),
+// so the items handed out last are the short ones: guided self-scheduling against the tail.
+struct Phase {
+    unsigned idx0;
+    int S, cps, pad;
+    long long pt0;
+    long long part0;  // offset (in doubles) of this phase's partial sums
+};
+constexpr int kMaxPhases = 8;
+
 struct KArgs {
     const rvl_model_desc *model;  // device copy
     const double *cols;           // [ncol][Npad]
     const uint8_t *inst;          // [Npad]
     const double *theta;          // [B][ndim]
-    double *lnl;                  // [B]        (written directly when S == 1)
-    double *partial;              // [B][S][2]  (S > 1)
-    int *flags;                   // [B] 1 = invalid Keplerian (S > 1, or written by the prepare pass)
+    double *lnl;                  // [B]
+    double *partial;              // per phase: [points][Sm*S][2] partial sums of the split points
+    int *arrive;                  // [split points] items of the point finished so far (self-resetting)
+    int *flags;                   // [B] 1 = invalid Keplerian (written by the prepare pass)
     const double *consts;         // [B][wstride] per-point constants from point_prepare_kernel, or NULL
     unsigned long long *counters; // 0 newton iters, 1 cap hits, 2 invalid points
-    unsigned int *work;           // [S] dynamic work counters
+    unsigned int *work;           // [Sm] dynamic work counters, [Sm] = blocks finished (self-resetting)
     long long B;
-    double cte;  // -0.5 N ln(2 pi)
+    long long ptS0;  // first point that is split into more than one item
+    double cte;      // -0.5 N ln(2 pi)
     int N, Npad, ncol;
-    int S, cps;  // slices, chunks per slice
-    int wstride; // doubles per warp in the constant block
+    int Sm, cpm;     // resident epoch ranges ("memory slices": block b holds range b % Sm), chunks each
+    unsigned nitems; // compute items per queue
+    unsigned n_setup; // setup items that precede them in the queue (one split point each), or 0
+    unsigned seq;     // launch stamp of the `ready` flags
+    double *gconsts;  // [n_setup][wstride] constants of the split points, written by the setup items
+    unsigned *ready;  // [n_setup] seq*2 + invalid once the constants of the point are in gconsts
+    int nph;
+    int wstride;     // doubles per warp in the constant block
+    Phase ph[kMaxPhases];
+    PeerOut peers;
+    unsigned long long *trace;  // optional [grid*warps][4]: t_enter, t_ready, t_done (ns), items
 };
 
 // ---- shared-memory / TMA helpers (sm_90+ PTX) --------------------------------------------
@@ -100,6 +131,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
             "r"(smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
+{
+    int o;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+    return o;
 }
 
 __device__ __forceinline__ double par_of(const rvl_param &p, const double *row)
@@ -254,7 +302,15 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
 // ---- per-point setup: theta row -> per-warp constants (modelk :411-457, :181-192) ---------
 // lane p < K handles planet p; lane i < n_inst handles instrument i; lane 0 the drift/linpar
 // coefficients.  Returns (warp-uniform) whether the point is a valid Keplerian.
-__device__ __forceinline__ bool point_setup(const rvl_model_desc &m, const double *row,
+#ifndef RVL_SETUP_OUTLINE
+#define RVL_SETUP_OUTLINE 1
+#endif
+#if RVL_SETUP_OUTLINE
+#define RVL_SETUP_INLINE __noinline__
+#else
+#define RVL_SETUP_INLINE __forceinline__
+#endif
+__device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const double *row,
                                             double *wc, int lane)
 {
     const int K = m.n_planets;
@@ -317,6 +373,148 @@ __device__ __forceinline__ bool point_setup(const rvl_model_desc &m, const doubl
     return !__any_sync(kFull, bad);
 }
 
+// ---- the epochs [c_lo, c_hi) x 32 of one work item, for the warp's current point ---------------
+// Code generation note: the instruction selection of the Newton loop (coefficients as direct
+// constant-bank operands, branches on uniform registers) is sensitive to what is inlined around
+// it; with the setup-item consumer inlined next to it ptxas switched to LDCU-staged coefficients
+// and convergence barriers inside the loop (+10% instructions per trip, -5% on the whole
+// kernel).  point_setup and take_point_consts are therefore out of line; this function is
+// inlined by default (RVL_OUTLINE=1 moves it out of line too, at the price of spills around it).
+// The block-wide constants come from shared memory (HotCtx), the per-point constants from the
+// warp's block at a_wc.
+struct HotCtx {
+    double tol;
+    uint32_t a_t0, colb, a_inst0, lin0;  // shared-window addresses / strides of the epoch columns
+    int K, itmax, has_drift, drift_hi, nlin, n_inst, e_base0, N;
+};
+struct ItemSums {
+    double chi, prod;
+    int esum, iters, caps, ok;
+};
+
+#ifndef RVL_OUTLINE
+#define RVL_OUTLINE 0
+#endif
+#if RVL_OUTLINE
+#define RVL_ITEM_INLINE __noinline__
+#else
+#define RVL_ITEM_INLINE __forceinline__
+#endif
+template <int VARIANT, int U>
+__device__ RVL_ITEM_INLINE ItemSums item_epochs(const HotCtx *hc, uint32_t a_wc, int c_lo, int c_hi,
+                                             int lane)
+{
+    const double tol = hc->tol;
+    const int K = hc->K, itmax = hc->itmax, drift_hi = hc->drift_hi, nlin = hc->nlin, N = hc->N;
+    const bool has_drift = hc->has_drift != 0;
+    const uint32_t a_ic = a_wc + (uint32_t)(K * kPlanetStride) * 8u;
+    const uint32_t a_dc = a_ic + (uint32_t)(2 * hc->n_inst) * 8u;
+    const uint32_t a_t = hc->a_t0 + (uint32_t)lane * 8u;
+    const uint32_t colb = hc->colb;
+    const uint32_t a_inst = hc->a_inst0 + (uint32_t)lane;
+    const uint32_t lin0 = hc->lin0;
+    const int e_base = hc->e_base0 + lane;
+    double chi = 0.0, prod = 1.0;
+    int esum = 0, iters = 0, caps = 0;
+    bool ok = true;
+    for (int ch = c_lo; ch < c_hi; ch += U) {
+        // U chunks of 32 epochs; a missing last chunk repeats the previous one, masked
+        uint32_t off[U];
+        bool live[U];
+        double t[U], rvsum[U];
+        int it_l[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool have = (ch + u) < c_hi;
+            const int cu = have ? ch + u : ch;
+            off[u] = (uint32_t)cu * 256u;
+            live[u] = have && (e_base + cu * 32) < N;
+            t[u] = lds_f64(a_t + off[u]);
+            rvsum[u] = 0.0;
+            it_l[u] = 0;
+        }
+        int cap_l = 0;
+        for (int p = 0; p < K; ++p) {
+            double v[U];
+            solve_planet<VARIANT, U>(t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
+                                     itmax, v, it_l, cap_l);
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvsum[u] = (p == 0) ? v[u] : rvl::add(rvsum[u], v[u]);
+        }
+        caps += cap_l;  // (padded / repeated lanes included: a cap hit is a cap hit)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t ae = a_t + off[u];
+            const int ii = lds_u8(a_inst + off[u] / 8u);
+            const uint32_t ai = a_ic + (uint32_t)ii * 16u;
+            double rvm = lds_f64(ai);
+            if (K > 0) rvm = rvl::add(rvm, rvsum[u]);
+            if (has_drift) {
+                // lin*tt + quad*tt^2 + cub*tt^3 + quar*tt^4, left to right (:271); a
+                // coefficient that is absent from the model is an exact +0 term: skipped
+                const double tt = lds_f64(ae + 3u * colb);
+                double dr = rvl::mul(lds_f64(a_dc), tt);
+                if (drift_hi > 0) {
+                    const double t2 = rvl::mul(tt, tt);
+                    dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 8), t2));
+                    if (drift_hi > 1) {
+                        dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 16), rvl::mul(t2, tt)));
+                        if (drift_hi > 2)
+                            dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 24), rvl::mul(t2, t2)));
+                    }
+                }
+                rvm = rvl::add(rvm, dr);
+            }
+            for (int l = 0; l < nlin; ++l)
+                rvm = rvl::add(rvm, rvl::mul(lds_f64(a_dc + 32u + (uint32_t)l * 8u),
+                                             lds_f64(ae + lin0 + (uint32_t)l * colb)));
+            const double res = rvl::sub(lds_f64(ae + colb), rvm);
+            const double var = rvl::add(lds_f64(ae + 2u * colb), lds_f64(ai + 8));
+            const double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
+            double mant;
+            int ex;
+            const bool okv = rvl::split_pos(var, mant, ex);
+            if (live[u]) {
+                chi = rvl::add(chi, term);
+                prod = rvl::mul(prod, mant);
+                esum += ex;
+                ok = ok && okv;
+                iters += it_l[u];
+            }
+        }
+        if (((ch - c_lo) & 255) >= 254) {  // keep the mantissa product in range
+            double mm;
+            int ee;
+            rvl::split_pos(prod, mm, ee);
+            prod = mm;
+            esum += ee;
+        }
+    }
+    return ItemSums{chi, prod, esum, iters, caps, ok ? 1 : 0};
+}
+
+// Constants of a split point, published by a setup item: into the warp's block in shared memory.
+// (pf_flag, pf0, pf1) is what the previous item requested ahead of time; if the point was not
+// ready then, wait for its flag (the setup item is in flight on some warp) and load again.
+// Out of line on purpose (see item_epochs).
+__device__ __noinline__ unsigned take_point_consts(const double *src, const unsigned *flagp,
+                                                   unsigned seq, double *wc, int wstride, int lane,
+                                                   unsigned pf_flag, double pf0, double pf1)
+{
+    if ((pf_flag >> 1) != seq) {
+        do {
+            pf_flag = ld_acquire_u32(flagp);
+        } while ((pf_flag >> 1) != seq);
+        pf0 = lane < wstride ? __ldcg(src + lane) : 0.0;
+        pf1 = lane + 32 < wstride ? __ldcg(src + lane + 32) : 0.0;
+    }
+    if (lane < wstride) wc[lane] = pf0;
+    if (lane + 32 < wstride) wc[lane + 32] = pf1;
+    for (int i = lane + 64; i < wstride; i += 32) wc[i] = __ldcg(src + i);
+    __syncwarp();
+    return pf_flag;
+}
+
 // ---- the likelihood kernel ------------------------------------------------------------------
 // U = epochs per lane in flight (1: 1024 threads/SM at <=64 registers; 2: 512 threads/SM at
 // <=128 registers, two chunks of 32 epochs per warp trip).
@@ -324,13 +522,16 @@ template <int VARIANT, int U, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [0,8) mbarrier | [128, 128+sizeof(model)) model | epoch columns | inst ids | warp consts
+    // [0,8) mbarrier, [16,128) HotCtx | [128, 128+sizeof(model)) model | epoch columns | inst ids |
+    // warp consts
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    HotCtx *hc = reinterpret_cast<HotCtx *>(smem_raw + 16);
+    static_assert(sizeof(HotCtx) <= 112, "HotCtx must fit in front of the model description");
     rvl_model_desc *sm = reinterpret_cast<rvl_model_desc *>(smem_raw + 128);
-    const int sl = blockIdx.x % a.S;
+    const int sl = blockIdx.x % a.Sm;
     const int Ctot = a.Npad / 32;
-    const int c0 = sl * a.cps;
-    const int nch = min(a.cps, Ctot - c0);  // chunks in this slice (>= 1 by construction)
+    const int c0 = sl * a.cpm;
+    const int nch = min(a.cpm, Ctot - c0);  // chunks resident in this block (>= 1 by construction)
     const int ne = nch * 32;
     double *scol = reinterpret_cast<double *>(smem_raw + 128 + kModelBytes);
     uint8_t *sinst = reinterpret_cast<uint8_t *>(scol + (size_t)a.ncol * ne);
@@ -338,6 +539,12 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
         smem_raw + 128 + kModelBytes + (((size_t)a.ncol * ne * 8 + ne + 127) / 128) * 128);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned n_items = 0;
+    if (a.trace && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 4] = t;
+    }
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -380,17 +587,63 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     const uint32_t colb = (uint32_t)ne * 8u;  // bytes per column
     const uint32_t a_inst = smem_u32(sinst) + (uint32_t)lane;
     const uint32_t lin0 = (uint32_t)(3 + (has_drift ? 1 : 0)) * colb;
-    const int e_base = c0 * 32 + lane;  // global epoch index of this lane in chunk 0
+    if (tid == 0) {
+        hc->tol = tol; hc->a_t0 = smem_u32(scol); hc->colb = colb; hc->a_inst0 = smem_u32(sinst);
+        hc->lin0 = lin0; hc->K = K; hc->itmax = itmax; hc->has_drift = has_drift ? 1 : 0;
+        hc->drift_hi = drift_hi; hc->nlin = nlin; hc->n_inst = m.n_inst;
+        hc->e_base0 = c0 * 32;  // global epoch index of lane 0 in chunk 0
+        hc->N = a.N;
+    }
+    __syncthreads();
 
     unsigned long long tot_iters = 0, tot_caps = 0, tot_invalid = 0;
+    if (a.trace && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 4 + 1] = t;
+    }
 
-    // work queue of this slice: the index of the NEXT item is requested while the current one is
-    // computed, so the atomic's round trip (~1 us) is off the critical path
+    // work queue of this epoch range: the index of the NEXT item is requested while the current
+    // one is computed, so the atomic's round trip (~1 us) is off the critical path
     unsigned idx = 0;
     if (lane == 0) idx = atomicAdd(&a.work[sl], 1u);
     idx = __shfl_sync(kFull, idx, 0);
-    while ((long long)idx < a.B) {
-        const long long pt = idx;
+
+    // ---- setup items (they come first in the queue): the per-point constants of the points that
+    // are cut into several work items are derived ONCE, by whichever warp draws the item, and
+    // published through `ready`.  Consumers can only ever wait for a warp that is already running.
+    while (idx < a.n_setup) {
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(&a.work[sl], 1u);
+        const long long pt = a.ptS0 + (long long)idx;
+        const bool valid =
+            point_setup(m, a.theta + pt * m.ndim, a.gconsts + (size_t)idx * a.wstride, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(a.ready + idx, a.seq * 2u + (valid ? 0u : 1u));
+        idx = __shfl_sync(kFull, next, 0);
+    }
+    idx -= a.n_setup;
+
+    // item -> (point, sub-slice of the resident chunks); all warp-uniform.  The item is carried as
+    // (phase | sub-slice << 3, index of the point within the phase): few registers across the
+    // hot loop; everything else is re-derived from the phase table in the constant bank.
+    unsigned it_ks = 0, it_jp = 0;
+    auto decode = [&](unsigned i) {
+        int k = 0;
+        while (k + 1 < a.nph && i >= a.ph[k + 1].idx0) ++k;
+        const unsigned Sk = (unsigned)a.ph[k].S;
+        const unsigned j = i - a.ph[k].idx0;
+        it_jp = j / Sk;
+        it_ks = (unsigned)k | ((j - it_jp * Sk) << 3);
+    };
+    if (idx < a.nitems) decode(idx);
+    // constants of the NEXT item, requested before the current item's reduction
+    unsigned pf_flag = 0;
+    double pf0 = 0.0, pf1 = 0.0;
+    bool pf_have = false;
+    while (idx < a.nitems) {
+        const long long pt = a.ph[it_ks & 7u].pt0 + (long long)it_jp;
         const double *row = a.theta + pt * m.ndim;
         unsigned next = 0;
         if (lane == 0) next = atomicAdd(&a.work[sl], 1u);
@@ -402,86 +655,45 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
             for (int i = lane; i < a.wstride; i += 32) wc[i] = __ldg(src + i);
             valid = __ldg(a.flags + pt) == 0;
             __syncwarp();
+        } else if (a.n_setup && pt >= a.ptS0) {  // published by a setup item
+            const unsigned si = (unsigned)(pt - a.ptS0);
+            const double *src = a.gconsts + (size_t)si * a.wstride;
+            pf_flag = take_point_consts(src, a.ready + si, a.seq, wc, a.wstride, lane,
+                                        pf_have ? pf_flag : 0u, pf0, pf1);
+            // (a vote makes the flag provably warp-uniform for the compiler: the hot loop below
+            // must stay under uniform control flow)
+            valid = __all_sync(kFull, (pf_flag & 1u) == 0u);
         } else {
             valid = point_setup(m, row, wc, lane);
         }
+        // what the rest of this iteration needs of the current item (the item variables are
+        // re-used for the next one before the reduction)
+        const unsigned c_ks = it_ks, c_jp = it_jp;
+        const int c_lo = (int)(c_ks >> 3) * a.ph[c_ks & 7u].cps;
+        const int c_hi = min(nch, c_lo + a.ph[c_ks & 7u].cps);  // may be empty in a short last range
 
-        double chi = 0.0, prod = 1.0;
-        int esum = 0, iters = 0, caps = 0;
-        bool ok = true;
-        if (valid) {
-            for (int ch = 0; ch < nch; ch += U) {
-                // U chunks of 32 epochs; a missing last chunk repeats the previous one, masked
-                uint32_t off[U];
-                bool live[U];
-                double t[U], rvsum[U];
-                int it_l[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool have = (ch + u) < nch;
-                    const int cu = have ? ch + u : ch;
-                    off[u] = (uint32_t)cu * 256u;
-                    live[u] = have && (e_base + cu * 32) < a.N;
-                    t[u] = lds_f64(a_t + off[u]);
-                    rvsum[u] = 0.0;
-                    it_l[u] = 0;
-                }
-                int cap_l = 0;
-                for (int p = 0; p < K; ++p) {
-                    double v[U];
-                    solve_planet<VARIANT, U>(t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
-                                             itmax, v, it_l, cap_l);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) rvsum[u] = (p == 0) ? v[u] : rvl::add(rvsum[u], v[u]);
-                }
-                caps += cap_l;  // (padded / repeated lanes included: a cap hit is a cap hit)
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t ae = a_t + off[u];
-                    const int ii = lds_u8(a_inst + off[u] / 8u);
-                    const uint32_t ai = a_ic + (uint32_t)ii * 16u;
-                    double rvm = lds_f64(ai);
-                    if (K > 0) rvm = rvl::add(rvm, rvsum[u]);
-                    if (has_drift) {
-                        // lin*tt + quad*tt^2 + cub*tt^3 + quar*tt^4, left to right (:271); a
-                        // coefficient that is absent from the model is an exact +0 term: skipped
-                        const double tt = lds_f64(ae + 3u * colb);
-                        double dr = rvl::mul(lds_f64(a_dc), tt);
-                        if (drift_hi > 0) {
-                            const double t2 = rvl::mul(tt, tt);
-                            dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 8), t2));
-                            if (drift_hi > 1) {
-                                dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 16), rvl::mul(t2, tt)));
-                                if (drift_hi > 2)
-                                    dr = rvl::add(dr, rvl::mul(lds_f64(a_dc + 24), rvl::mul(t2, t2)));
-                            }
-                        }
-                        rvm = rvl::add(rvm, dr);
-                    }
-                    for (int l = 0; l < nlin; ++l)
-                        rvm = rvl::add(rvm, rvl::mul(lds_f64(a_dc + 32u + (uint32_t)l * 8u),
-                                                     lds_f64(ae + lin0 + (uint32_t)l * colb)));
-                    const double res = rvl::sub(lds_f64(ae + colb), rvm);
-                    const double var = rvl::add(lds_f64(ae + 2u * colb), lds_f64(ai + 8));
-                    const double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
-                    double mant;
-                    int ex;
-                    const bool okv = rvl::split_pos(var, mant, ex);
-                    if (live[u]) {
-                        chi = rvl::add(chi, term);
-                        prod = rvl::mul(prod, mant);
-                        esum += ex;
-                        ok = ok && okv;
-                        iters += it_l[u];
-                    }
-                }
-                if ((ch & 255) == 254 || (ch & 255) == 255) {  // keep the mantissa product in range
-                    double mm;
-                    int ee;
-                    rvl::split_pos(prod, mm, ee);
-                    prod = mm;
-                    esum += ee;
-                }
+        // ---- the item's epochs: Kepler solves + Gaussian terms (out of line, see item_epochs) ----
+        ItemSums sums{0.0, 1.0, 0, 0, 0, 1};
+        if (valid) sums = item_epochs<VARIANT, U>(hc, a_wc, c_lo, c_hi, lane);
+        double chi = sums.chi, prod = sums.prod;
+        int esum = sums.esum;
+        const int iters = sums.iters, caps = sums.caps;
+        const bool ok = sums.ok != 0;
+
+        // ---- next item: decode it and request its constants now, so that they arrive while this
+        // item's sums are being reduced
+        idx = __shfl_sync(kFull, next, 0) - a.n_setup;
+        pf_have = false;
+        if (idx < a.nitems) {
+            decode(idx);
+            const long long npt = a.ph[it_ks & 7u].pt0 + (long long)it_jp;
+            if (a.n_setup && npt >= a.ptS0) {
+                const unsigned si = (unsigned)(npt - a.ptS0);
+                const double *src = a.gconsts + (size_t)si * a.wstride;
+                pf_flag = ld_acquire_u32(a.ready + si);
+                pf0 = lane < a.wstride ? __ldcg(src + lane) : 0.0;
+                pf1 = lane + 32 < a.wstride ? __ldcg(src + lane + 32) : 0.0;
+                pf_have = true;
             }
         }
 
@@ -510,9 +722,9 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
             } else {
                 // a variance that is zero / subnormal / negative / non-finite: plain logs
                 double acc = 0.0;
-                for (int ch = 0; ch < nch; ++ch) {
+                for (int ch = c_lo; ch < c_hi; ++ch) {
                     const uint32_t o8 = (uint32_t)ch * 256u;
-                    if ((e_base + ch * 32) < a.N) {
+                    if ((c0 * 32 + lane + ch * 32) < a.N) {
                         const int ii = lds_u8(a_inst + o8 / 8u);
                         const double var = rvl::add(lds_f64(a_t + o8 + 2u * colb),
                                                     lds_f64(a_ic + (uint32_t)ii * 16u + 8u));
@@ -532,45 +744,90 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
         } else {
             S1 = 0.0;
             S2 = 0.0;
-            if (sl == 0) ++tot_invalid;
+            if (sl == 0 && (c_ks >> 3) == 0u) ++tot_invalid;
         }
-        if (lane == 0) {
-            if (a.S == 1) {
-                // (cte - sum ln sqrt var) - sum r^2/(2 var)   (:80); invalid -> -1e30 (:203)
-                a.lnl[pt] = valid ? rvl::sub(rvl::sub(a.cte, S1), S2) : -1e30;
-            } else {
-                // this slice's partial sums; combine_slices_kernel adds them in slice order
-                double *o = a.partial + ((size_t)pt * a.S + sl) * 2;
-                o[0] = S1;
-                o[1] = S2;
+        const int c_k = (int)(c_ks & 7u), c_Sk = a.ph[c_ks & 7u].S, c_ss = (int)(c_ks >> 3);
+        const long long c_pt = a.ph[c_k].pt0 + (long long)c_jp;
+        const int Stot = a.Sm * c_Sk;  // items of this point
+        bool finish = Stot == 1;
+        if (!finish) {
+            // this item's partial sums; the item that arrives LAST adds all of them in epoch order
+            // (deterministic) -- no second kernel
+            const int slot = sl * c_Sk + c_ss;
+            double *pp = a.partial + a.ph[c_k].part0 + (size_t)c_jp * (size_t)Stot * 2;
+            int *arr = a.arrive + (c_pt - a.ptS0);
+            int old = 0;
+            if (lane == 0) {
+                pp[2 * slot] = S1;
+                pp[2 * slot + 1] = S2;
+                old = atom_add_acq_rel(arr, 1);  // release: the two stores above are visible first
+            }
+            old = __shfl_sync(kFull, old, 0);
+            if (old == Stot - 1) {
+                finish = true;
+                if (lane == 0) *arr = 0;  // ready for the next launch
+                __threadfence();
+                S1 = 0.0;
+                S2 = 0.0;
+                for (int base = 0; base < Stot; base += 32) {
+                    double v1 = 0.0, v2 = 0.0;
+                    if (base + lane < Stot) {
+                        v1 = __ldcg(pp + 2 * (base + lane));
+                        v2 = __ldcg(pp + 2 * (base + lane) + 1);
+                    }
+                    const int n = min(32, Stot - base);
+                    for (int i = 0; i < n; ++i) {
+                        S1 = rvl::add(S1, __shfl_sync(kFull, v1, i));
+                        S2 = rvl::add(S2, __shfl_sync(kFull, v2, i));
+                    }
+                }
             }
         }
-        idx = __shfl_sync(kFull, next, 0);
+        if (finish && lane == 0) {
+            // (cte - sum ln sqrt var) - sum r^2/(2 var)   (:80); invalid -> -1e30 (:203)
+            const double v = valid ? rvl::sub(rvl::sub(a.cte, S1), S2) : -1e30;
+            a.lnl[c_pt] = v;
+            // fused all-gather: the value goes straight into every rank's gathered vector (NVLink)
+            for (int r = 0; r < a.peers.n; ++r) a.peers.ptr[r][a.peers.offset + c_pt] = v;
+        }
+        ++n_items;
+    }
+    if (a.trace && lane == 0) {
+        unsigned long long t_done;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
+        unsigned long long *o = a.trace + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 4;
+        o[2] = t_done; o[3] = n_items;
     }
     if (lane == 0) {
         if (tot_iters) atomicAdd(&a.counters[0], tot_iters);
         if (tot_caps) atomicAdd(&a.counters[1], tot_caps);
         if (tot_invalid) atomicAdd(&a.counters[2], tot_invalid);
     }
+    // the last block to leave re-arms the work counters for the next launch on this handle
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&a.work[a.Sm], 1u) == gridDim.x - 1) {
+            for (int i = 0; i <= a.Sm; ++i) a.work[i] = 0u;
+        }
+    }
 }
 
 // ---- once-per-point pass: (optional) unit cube -> theta, then the per-point constants ----------
 // One warp per point.  With U != NULL this is the fused prior transform: lane i < ndim evaluates
 // ppf_i(u_i), theta is written out (the sampler stores it) and the constants are derived from
-// exactly those values.  Used whenever the epoch axis is cut into S > 1 slices (the constants are
-// then computed once per point instead of once per slice) and for rvl_transform_loglike.
+// exactly those values.  Used for rvl_transform_loglike (and on request, option "prepare"): the
+// likelihood kernel otherwise derives the constants itself, per work item.
 __device__ double ppf_eval(const rvl_prior_desc &pr, const double *tables, double q);
 
 __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc *model,
                                                             const rvl_prior_desc *priors,
                                                             const double *tables, const double *U,
                                                             double *theta, double *consts,
-                                                            int *flags,
-                                                            unsigned int *work, int n_work,
-                                                            long long B, int wstride)
+                                                            int *flags, long long B,
+                                                            int wstride)
 {
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x < n_work) work[threadIdx.x] = 0u;  // per-slice work queues
     // the model description is read many times per point: one cooperative copy to shared memory
     __shared__ __align__(16) unsigned char s_model[sizeof(rvl_model_desc)];
     {
@@ -599,46 +856,6 @@ __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc
     __syncwarp();
     const bool valid = point_setup(m, srow, consts + (size_t)pt * wstride, lane);
     if (lane == 0) flags[pt] = valid ? 0 : 1;
-}
-
-// Peer buffers of the fused all-gather: device pointers into the other ranks' (and our own)
-// gathered lnL vectors (NVLink peer / symmetric memory).  Passed by value.
-struct PeerOut {
-    double *ptr[RVL_MAX_PEERS];
-    int n;
-    long long offset;  // element offset of this rank's block inside every gathered vector
-};
-
-// combine the per-slice partial sums in slice order (deterministic):
-// lnL = (cte - sum_s S1) - sum_s S2  (:80); invalid Keplerian -> -1e30 (:203).
-// With peers: the result is also stored straight into every rank's gathered vector over
-// NVLink -- the all-gather is fused into the producing kernel.
-__global__ void combine_slices_kernel(const double *partial, const int *flags, double *lnl,
-                                      long long B, int S, double cte, const PeerOut peers)
-{
-    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pt >= B) return;
-    double v = -1e30;
-    if (!flags[pt]) {
-        const double *p = partial + (size_t)pt * S * 2;
-        double s1 = 0.0, s2 = 0.0;
-        for (int s = 0; s < S; ++s) {
-            s1 = rvl::add(s1, p[2 * s]);
-            s2 = rvl::add(s2, p[2 * s + 1]);
-        }
-        v = rvl::sub(rvl::sub(cte, s1), s2);
-    }
-    lnl[pt] = v;
-    for (int r = 0; r < peers.n; ++r) peers.ptr[r][peers.offset + pt] = v;
-}
-
-// S == 1 (the likelihood kernel wrote lnL itself): push the finished block to the peers
-__global__ void scatter_peers_kernel(const double *lnl, long long B, const PeerOut peers)
-{
-    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pt >= B) return;
-    const double v = lnl[pt];
-    for (int r = 0; r < peers.n; ++r) peers.ptr[r][peers.offset + pt] = v;
 }
 
 // ---- prior transform: unit cube -> theta (evidence/ultranest/__init__.py:125-137) -----------
@@ -800,17 +1017,34 @@ struct rvl_handle {
     int prior_ndim = 0;
 
     // per-call scratch (grown on demand)
-    long long cap_B = 0, cap_flags = 0;
+    long long cap_B = 0, cap_flags = 0, cap_arrive = 0;
     size_t cap_partial = 0;
+    int *d_arrive = nullptr;
+    double *d_gconsts = nullptr;   // constants of the split points (written by the setup items)
+    unsigned *d_ready = nullptr;   // their launch-stamped ready flags
+    size_t cap_gconsts = 0;
+    long long cap_ready = 0;
+    unsigned seq = 0;
+    unsigned long long *d_trace = nullptr;  // option "trace": per-warp time stamps of the last launch
+    int trace_rows = 0;
     double *d_theta = nullptr, *d_u = nullptr, *d_lnl = nullptr, *d_partial = nullptr;
     double *d_consts = nullptr;
     size_t cap_consts = 0;
     int *d_flags = nullptr;
     unsigned long long *d_counters = nullptr;  // 3
-    unsigned int *d_work = nullptr;            // sm_count
+    unsigned int *d_work = nullptr;            // sm_count + 1 (queues, finished-block counter)
 
     // options
     int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 0, opt_zero_copy = 1, opt_ilp = 2, opt_min_chunks = 8, opt_items_per_warp = 4;
+    int opt_sched = 1;          // 1: graded phases (coarse -> fine items), 0: one uniform slice count
+    int opt_phase_items = 200;  // items per split phase, in percent of the warps serving a queue
+    int opt_max_split = 8;      // finest cut: sub-slices per point and resident range
+                                // (B200, config 2 at ndraw = 4096: 127 us against 130 us for a
+                                // uniform cut in 4 and 159 us with whole-point items first;
+                                // every item costs ~430 warp-instructions on top of its epochs)
+    int opt_trace = 0;
+    int opt_setup_items = 1;    // 1: constants of split points from setup items inside the kernel
+    int opt_prepare = 0;        // 1: per-point constants from the prepare pass even without a transform
 
     // bookkeeping
     uint64_t n_points = 0, n_solves = 0, launches = 0;
@@ -888,22 +1122,30 @@ int ensure_io(rvl_t *h, long long B)
     return RVL_OK;
 }
 
-// per-slice partial sums (S > 1), invalid-point flags and prepared per-point constants
-int ensure_partial(rvl_t *h, long long B, int S, bool prepare, int wstride)
+// partial sums and arrival counters of the split points, invalid-point flags and prepared
+// per-point constants
+int ensure_partial(rvl_t *h, long long B, size_t partial_doubles, long long n_split, bool prepare,
+                   int wstride)
 {
-    if (S <= 1 && !prepare) return RVL_OK;
-    if (B > h->cap_flags) {
+    if (prepare && B > h->cap_flags) {
         cudaFree(h->d_flags);
         h->d_flags = nullptr; h->cap_flags = 0;
         CU(h, cudaMalloc(&h->d_flags, (size_t)B * sizeof(int)));
         h->cap_flags = B;
     }
-    const size_t need = (size_t)B * S;
-    if (S > 1 && need > h->cap_partial) {
+    if (partial_doubles > h->cap_partial) {
         cudaFree(h->d_partial);
         h->d_partial = nullptr; h->cap_partial = 0;
-        CU(h, cudaMalloc(&h->d_partial, need * 2 * sizeof(double)));
-        h->cap_partial = need;
+        CU(h, cudaMalloc(&h->d_partial, partial_doubles * sizeof(double)));
+        h->cap_partial = partial_doubles;
+    }
+    if (n_split > h->cap_arrive) {
+        cudaFree(h->d_arrive);
+        h->d_arrive = nullptr; h->cap_arrive = 0;
+        CU(h, cudaMalloc(&h->d_arrive, (size_t)n_split * sizeof(int)));
+        // zero once: the kernel leaves every counter at zero again (last arriver resets it)
+        CU(h, cudaMemset(h->d_arrive, 0, (size_t)n_split * sizeof(int)));
+        h->cap_arrive = n_split;
     }
     const size_t needc = (size_t)B * wstride;
     if (prepare && needc > h->cap_consts) {
@@ -916,8 +1158,13 @@ int ensure_partial(rvl_t *h, long long B, int S, bool prepare, int wstride)
 }
 
 struct Plan {
-    int S, cps, W, U, grid, wstride;
+    int Sm, cpm, W, U, grid, wstride;
     size_t smem;
+    int nph;
+    Phase ph[kMaxPhases];
+    unsigned nitems;
+    long long ptS0, n_split;
+    size_t partial_doubles;
 };
 
 size_t smem_need(int ncol, int ne, int W, int wstride)
@@ -926,41 +1173,110 @@ size_t smem_need(int ncol, int ne, int W, int wstride)
            (size_t)W * wstride * 8;
 }
 
+// Work decomposition.  The epoch axis is cut into Sm resident ranges (the fewest that fit in
+// shared memory; block b holds range b % Sm and serves that range's queue).  Within a range a
+// point is one item, or -- for the points at the END of the batch -- 2, 4, ... sub-slices, each
+// phase holding about one item per warp: the work handed out last is the finest, so all warps of
+// the chip run dry together (a batch of ndraw = 4096 points is ONE point per warp otherwise).
+struct PlanIn {
+    int Ctot, ncol, wstride, U, W, sm_count, smem_optin;
+    int sched, slices, items_per_warp, min_chunks, phase_items, max_split;
+};
+
+const char *plan_core(const PlanIn &in, long long B, Plan &pl)
+{
+    const PlanIn *h = &in;
+    const int Ctot = in.Ctot, wstride = in.wstride, U = in.U, W = in.W;
+    int Sm = 1, cpm = 0;
+    auto cpm_of = [&](int s) { return ((Ctot + s - 1) / s + U - 1) / U * U; };  // whole U-chunk trips
+    auto fits = [&](int s) {
+        return smem_need(h->ncol, cpm_of(s) * 32, W, wstride) <= (size_t)h->smem_optin;
+    };
+    while (Sm < Ctot && Sm < h->sm_count && !fits(Sm)) ++Sm;
+    if (!fits(Sm)) return "epoch range does not fit in shared memory";
+    cpm = cpm_of(Sm);
+    Sm = (Ctot + cpm - 1) / cpm;  // drop empty trailing ranges
+    pl.Sm = Sm; pl.cpm = cpm; pl.W = W; pl.U = U; pl.wstride = wstride;
+    pl.grid = std::max(1, h->sm_count / Sm) * Sm;
+    pl.smem = smem_need(h->ncol, cpm * 32, W, wstride);
+
+    // sub-slice counts available within one resident range: S -> cps = ceil(cpm / S) in whole trips
+    auto cps_of = [&](int S) { return ((cpm + S - 1) / S + U - 1) / U * U; };
+    auto norm = [&](int S) { const int c = cps_of(S); return (cpm + c - 1) / c; };
+    const long long warps_q = (long long)(pl.grid / Sm) * W;  // warps serving one queue
+    pl.nph = 0;
+    pl.ptS0 = B; pl.n_split = 0; pl.partial_doubles = 0;
+    struct Seg { int S; long long n; };
+    Seg seg[kMaxPhases];
+    int nseg = 0;
+    long long left = B;
+    if (h->slices > 0 || !h->sched) {
+        // one uniform slice count for every point
+        long long want;
+        if (h->slices > 0) want = (h->slices + Sm - 1) / Sm;
+        else {
+            want = ((long long)h->items_per_warp * warps_q + B - 1) / std::max<long long>(B, 1);
+            want = std::min<long long>(want, std::max(1, cpm / h->min_chunks));
+        }
+        const int S = norm((int)std::max<long long>(1, std::min<long long>(want, cpm)));
+        seg[nseg++] = Seg{S, B};
+        left = 0;
+    } else {
+        // graded: finest phase last; built from the end of the batch backwards
+        int Smax = norm(std::max(1, std::min(h->max_split, cpm)));
+        const long long per_phase = std::max<long long>(1, warps_q * h->phase_items / 100);
+        Seg rev[kMaxPhases];
+        int nrev = 0;
+        for (int S = Smax; S > 1 && left > 0 && nrev < kMaxPhases - 1; S = norm(S / 2)) {
+            const long long n = std::min(left, std::max<long long>(1, per_phase / S));
+            if (nrev > 0 && rev[nrev - 1].S == S) rev[nrev - 1].n += n;
+            else rev[nrev++] = Seg{S, n};
+            left -= n;
+            if (norm(S / 2) >= S) break;
+        }
+        if (left > 0) rev[nrev++] = Seg{1, left};
+        left = 0;
+        for (int i = nrev - 1; i >= 0; --i) seg[nseg++] = rev[i];
+    }
+    unsigned long long idx = 0;
+    long long pt = 0;
+    size_t part = 0;
+    for (int i = 0; i < nseg; ++i) {
+        Phase &p = pl.ph[pl.nph++];
+        p.idx0 = (unsigned)idx; p.S = seg[i].S; p.cps = cps_of(seg[i].S); p.pad = 0;
+        p.pt0 = pt; p.part0 = (long long)part;
+        const int Stot = Sm * seg[i].S;
+        if (Stot > 1) {
+            if (pl.n_split == 0) pl.ptS0 = pt;
+            pl.n_split += seg[i].n;
+            part += (size_t)seg[i].n * Stot * 2;
+        } else if (pl.n_split > 0) {
+            return "internal: whole-point phase after a split phase";
+        }
+        idx += (unsigned long long)seg[i].n * seg[i].S;
+        pt += seg[i].n;
+    }
+    if (idx > 0xfffffff0ULL) return "batch too large for one call";
+    pl.nitems = (unsigned)idx;
+    pl.partial_doubles = part;
+    return nullptr;
+}
+
 int make_plan(rvl_t *h, long long B, Plan &pl)
 {
     const rvl_model_desc &m = h->model;
-    const int Ctot = h->Npad / 32;
-    int wstride = m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar;
-    wstride = (wstride + 1) & ~1;
-    const int U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
-    int W = h->opt_warps > 0 ? h->opt_warps : (U == 2 ? 28 : 32);
-    W = std::max(1, std::min(32, W));
-    // smallest slice count whose slice fits in shared memory
-    int S = 1;
-    auto fits = [&](int s) {
-        const int cps = (Ctot + s - 1) / s;
-        return smem_need(h->ncol, cps * 32, W, wstride) <= (size_t)h->smem_optin;
-    };
-    while (S < Ctot && !fits(S)) ++S;
-    if (!fits(S)) return fail(h, RVL_EINVAL, "epoch chunk does not fit in shared memory");
-    if (h->opt_slices > 0) {
-        S = std::max(S, std::min(h->opt_slices, Ctot));
-    } else {
-        // small batches: cut epochs finer so that every warp of the chip gets >= ~4 work items,
-        // but keep >= 8 chunks per slice so the per-point setup stays amortised
-        const long long warps_total = (long long)h->sm_count * W;
-        long long want = ((long long)h->opt_items_per_warp * warps_total + B - 1) / std::max<long long>(B, 1);
-        const int maxS = std::max(1, Ctot / h->opt_min_chunks);
-        S = std::max<long long>(S, std::min<long long>(want, maxS));
-    }
-    S = std::min(S, h->sm_count);
-    int cps = (Ctot + S - 1) / S;
-    S = (Ctot + cps - 1) / cps;  // drop empty trailing slices
-    if (!fits(S)) return fail(h, RVL_EINVAL, "slice does not fit in shared memory");
-    pl.S = S; pl.cps = cps; pl.W = W; pl.U = U; pl.wstride = wstride;
-    pl.grid = std::max(1, h->sm_count / S) * S;
-    pl.smem = smem_need(h->ncol, cps * 32, W, wstride);
-    return RVL_OK;
+    PlanIn in{};
+    in.Ctot = h->Npad / 32;
+    in.ncol = h->ncol;
+    in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1) & ~1;
+    in.U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
+    in.W = std::max(1, std::min(32, h->opt_warps > 0 ? h->opt_warps : (in.U == 2 ? 28 : 32)));
+    in.sm_count = h->sm_count; in.smem_optin = h->smem_optin;
+    in.sched = h->opt_sched; in.slices = h->opt_slices; in.items_per_warp = h->opt_items_per_warp;
+    in.min_chunks = h->opt_min_chunks; in.phase_items = h->opt_phase_items;
+    in.max_split = h->opt_max_split;
+    const char *e = plan_core(in, B, pl);
+    return e ? fail(h, RVL_EINVAL, e) : RVL_OK;
 }
 
 template <int V, int U, int T>
@@ -977,7 +1293,8 @@ int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
 // device pointers.  dU != NULL: fused prior transform -- theta is WRITTEN to dTheta by the prepare
 // pass and the likelihood is evaluated on exactly those values.
 int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, double *dlnL,
-                    cudaStream_t st, bool timed, const PeerOut *peers = nullptr)
+                    cudaStream_t st, bool timed, const PeerOut *peers = nullptr,
+                    bool force_prepare = false)
 {
     if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
     if (dU && !h->have_priors) return fail(h, RVL_ESTATE, "set priors first");
@@ -988,25 +1305,55 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     Plan pl;
     int rc = make_plan(h, B, pl);
     if (rc) return rc;
-    const bool prepare = pl.S > 1 || dU != nullptr;
-    rc = ensure_partial(h, B, pl.S, prepare, pl.wstride);
+    const bool prepare = dU != nullptr || h->opt_prepare || force_prepare;
+    rc = ensure_partial(h, B, pl.partial_doubles, pl.n_split, prepare, pl.wstride);
     if (rc) return rc;
     if (prepare) {
         const int wpb = 8;  // warps (= points) per block
         point_prepare_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-            h->d_model, h->d_priors, h->d_tables, dU, dTheta, h->d_consts, h->d_flags,
-            h->d_work, h->sm_count, B, pl.wstride);
+            h->d_model, h->d_priors, h->d_tables, dU, dTheta, h->d_consts, h->d_flags, B,
+            pl.wstride);
         CU(h, cudaGetLastError());
         ++h->launches;
-    } else {
-        CU(h, cudaMemsetAsync(h->d_work, 0, sizeof(unsigned) * (size_t)h->sm_count, st));
+    }
+    const bool setup_items = !prepare && h->opt_setup_items && pl.Sm == 1 && pl.n_split > 0 &&
+                             (unsigned long long)pl.nitems + (unsigned long long)pl.n_split < 0xfffffff0ULL;
+    if (setup_items) {
+        const size_t need = (size_t)pl.n_split * pl.wstride;
+        if (need > h->cap_gconsts) {
+            cudaFree(h->d_gconsts);
+            h->d_gconsts = nullptr; h->cap_gconsts = 0;
+            CU(h, cudaMalloc(&h->d_gconsts, need * sizeof(double)));
+            h->cap_gconsts = need;
+        }
+        if (pl.n_split > h->cap_ready || h->seq >= 0x7ffffff0u) {
+            cudaFree(h->d_ready);
+            h->d_ready = nullptr; h->cap_ready = 0;
+            const long long cap = std::max(pl.n_split, h->cap_ready);
+            CU(h, cudaMalloc(&h->d_ready, (size_t)cap * sizeof(unsigned)));
+            CU(h, cudaMemset(h->d_ready, 0, (size_t)cap * sizeof(unsigned)));  // stamp 0 = never
+            h->cap_ready = cap;
+            h->seq = 0;
+        }
+        ++h->seq;
     }
     KArgs a{};
+    a.n_setup = setup_items ? (unsigned)pl.n_split : 0u;
+    a.seq = h->seq; a.gconsts = h->d_gconsts; a.ready = h->d_ready;
     a.model = h->d_model; a.cols = h->d_cols; a.inst = h->d_inst; a.theta = dTheta; a.lnl = dlnL;
-    a.partial = h->d_partial; a.flags = h->d_flags; a.counters = h->d_counters; a.work = h->d_work;
+    a.partial = h->d_partial; a.arrive = h->d_arrive; a.flags = h->d_flags;
+    a.counters = h->d_counters; a.work = h->d_work;
     a.consts = prepare ? h->d_consts : nullptr;
-    a.B = B; a.cte = -0.5 * h->N * log(2 * M_PI); a.N = h->N; a.Npad = h->Npad; a.ncol = h->ncol;
-    a.S = pl.S; a.cps = pl.cps; a.wstride = pl.wstride;
+    a.B = B; a.ptS0 = pl.ptS0; a.cte = -0.5 * h->N * log(2 * M_PI); a.N = h->N; a.Npad = h->Npad;
+    a.ncol = h->ncol; a.Sm = pl.Sm; a.cpm = pl.cpm; a.nitems = pl.nitems; a.nph = pl.nph;
+    a.wstride = pl.wstride;
+    for (int i = 0; i < pl.nph; ++i) a.ph[i] = pl.ph[i];
+    if (peers) a.peers = *peers;
+    if (h->opt_trace) {
+        if (!h->d_trace) CU(h, cudaMalloc(&h->d_trace, (size_t)h->sm_count * 32 * 4 * sizeof(unsigned long long)));
+        a.trace = h->d_trace;
+        h->trace_rows = pl.grid * pl.W;
+    }
     if (timed) CU(h, cudaEventRecord(h->ev0, st));
     if (h->opt_variant == 1) rc = launch_lnl_v<1, 1, 1024>(h, a, pl, st);
     else if (pl.U == 2 && pl.W <= 16) rc = launch_lnl_v<0, 2, 512>(h, a, pl, st);
@@ -1018,19 +1365,6 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     if (rc) return rc;
     if (timed) { CU(h, cudaEventRecord(h->ev1, st)); h->timing_pending = true; }
     ++h->launches;
-    if (pl.S > 1) {
-        const int tb = 256;
-        PeerOut none{};
-        combine_slices_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(
-            h->d_partial, h->d_flags, dlnL, B, pl.S, a.cte, peers ? *peers : none);
-        CU(h, cudaGetLastError());
-        ++h->launches;
-    } else if (peers && peers->n > 0) {
-        const int tb = 256;
-        scatter_peers_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(dlnL, B, *peers);
-        CU(h, cudaGetLastError());
-        ++h->launches;
-    }
     h->n_points += (uint64_t)B;
     h->n_solves += (uint64_t)B * (uint64_t)h->N * (uint64_t)h->model.n_planets;
     return RVL_OK;
@@ -1115,7 +1449,9 @@ int rvl_create(rvl_t **out, int device)
     if ((ce = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("event", ce);
     if ((ce = cudaMalloc(&h->d_counters, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail("malloc", ce);
     if ((ce = cudaMemset(h->d_counters, 0, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail("memset", ce);
-    if ((ce = cudaMalloc(&h->d_work, sizeof(unsigned) * (size_t)h->sm_count)) != cudaSuccess) return bail("malloc", ce);
+    // work counters + finished-block counter: zero now, the kernel re-arms them when it ends
+    if ((ce = cudaMalloc(&h->d_work, sizeof(unsigned) * (size_t)(h->sm_count + 1))) != cudaSuccess) return bail("malloc", ce);
+    if ((ce = cudaMemset(h->d_work, 0, sizeof(unsigned) * (size_t)(h->sm_count + 1))) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMalloc(&h->d_model, sizeof(rvl_model_desc))) != cudaSuccess) return bail("malloc", ce);
     *out = h;
     return RVL_OK;
@@ -1129,7 +1465,8 @@ void rvl_destroy(rvl_t *h)
     cudaFree(h->d_cols); cudaFree(h->d_inst); cudaFree(h->d_model); cudaFree(h->d_priors);
     cudaFree(h->d_tables); cudaFree(h->d_theta); cudaFree(h->d_u); cudaFree(h->d_lnl);
     cudaFree(h->d_partial); cudaFree(h->d_flags); cudaFree(h->d_counters); cudaFree(h->d_work);
-    cudaFree(h->d_consts);
+    cudaFree(h->d_consts); cudaFree(h->d_arrive); cudaFree(h->d_trace);
+    cudaFree(h->d_gconsts); cudaFree(h->d_ready);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1240,9 +1577,15 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
     else if (n == "slices") h->opt_slices = (int)std::max<int64_t>(0, value);
     else if (n == "warps") h->opt_warps = (int)std::max<int64_t>(0, std::min<int64_t>(32, value));
     else if (n == "timing") h->opt_timing = value != 0;
-    else if (n == "zero_copy") h->opt_zero_copy = value != 0;
+    else if (n == "zero_copy") h->opt_zero_copy = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
     else if (n == "min_chunks") h->opt_min_chunks = (int)std::max<int64_t>(1, value);
     else if (n == "items_per_warp") h->opt_items_per_warp = (int)std::max<int64_t>(1, value);
+    else if (n == "sched") h->opt_sched = value != 0;
+    else if (n == "phase_items") h->opt_phase_items = (int)std::max<int64_t>(1, std::min<int64_t>(100000, value));
+    else if (n == "max_split") h->opt_max_split = (int)std::max<int64_t>(1, std::min<int64_t>(4096, value));
+    else if (n == "prepare") h->opt_prepare = value != 0;
+    else if (n == "trace") h->opt_trace = value != 0;
+    else if (n == "setup_items") h->opt_setup_items = value != 0;
     else if (n == "ilp") { if (value != 1 && value != 2) return fail(h, RVL_EINVAL, "ilp in {1,2}"); h->opt_ilp = (int)value; }
     else return fail(h, RVL_EINVAL, "unknown option " + n);
     return RVL_OK;
@@ -1302,20 +1645,20 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
     DevGuard g(h->device);
     int rc = ensure_io(h, B);
     if (rc) return rc;
-    // Pinned caller buffers are used in place (zero-copy) when the once-per-point prepare pass
-    // reads theta (one coalesced read per row); otherwise theta is staged with a copy.
-    Plan pl;
-    rc = make_plan(h, B, pl);
-    if (rc) return rc;
+    // A pinned theta is read in place (zero-copy) by the once-per-point prepare pass: one
+    // coalesced read per row over PCIe, constants left in HBM for the likelihood kernel (whose
+    // own per-item setup would read the row several times).  Pageable theta is staged by a copy.
+    // A pinned lnL is written in place.
     const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
-    double *th_dev = pl.S > 1 ? (double *)pinned_alias(h, Theta) : nullptr;
+    double *th_dev = h->opt_zero_copy > 1 ? (double *)pinned_alias(h, Theta) : nullptr;
     double *out_dev = (double *)pinned_alias(h, lnL);
+    const bool via_prepare = th_dev != nullptr;
     if (!th_dev) {
         th_dev = h->d_theta;
         if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
     }
     rc = enqueue_loglike(h, nullptr, th_dev, B, out_dev ? out_dev : h->d_lnl, h->stream,
-                         h->opt_timing != 0);
+                         h->opt_timing != 0, nullptr, via_prepare);
     if (rc) return rc;
     if (!out_dev)
         CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1466,6 +1809,40 @@ int rvl_fp64_peak(rvl_t *h, double *tflops)
     }
     cudaFree(out);
     *tflops = best;
+    return RVL_OK;
+}
+
+int rvl_read_trace(rvl_t *h, uint64_t *out, int32_t cap_rows, int32_t *rows)
+{
+    if (!h || !out || !rows) return RVL_EINVAL;
+    *rows = 0;
+    if (!h->d_trace || h->trace_rows <= 0) return fail(h, RVL_ESTATE, "no trace recorded (option \"trace\")");
+    if (cap_rows < h->trace_rows) return fail(h, RVL_EINVAL, "trace buffer too small");
+    DevGuard g(h->device);
+    CU(h, cudaDeviceSynchronize());
+    CU(h, cudaMemcpy(out, h->d_trace, (size_t)h->trace_rows * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *rows = h->trace_rows;
+    return RVL_OK;
+}
+
+int rvl_plan_describe(const int32_t *in, int64_t B, int64_t *out, int32_t cap)
+{
+    if (!in || !out || cap < 8) return RVL_EINVAL;
+    PlanIn pi{};
+    pi.Ctot = in[0]; pi.ncol = in[1]; pi.wstride = in[2]; pi.U = in[3]; pi.W = in[4];
+    pi.sm_count = in[5]; pi.smem_optin = in[6]; pi.sched = in[7]; pi.slices = in[8];
+    pi.items_per_warp = in[9]; pi.min_chunks = in[10]; pi.phase_items = in[11]; pi.max_split = in[12];
+    if (pi.Ctot < 1 || pi.U < 1 || pi.U > 2 || pi.W < 1 || pi.sm_count < 1 || B < 1) return RVL_EINVAL;
+    Plan pl{};
+    if (plan_core(pi, B, pl)) return RVL_EINVAL;
+    if (cap < 8 + 5 * pl.nph) return RVL_EINVAL;
+    out[0] = pl.Sm; out[1] = pl.cpm; out[2] = pl.grid; out[3] = pl.nph; out[4] = pl.nitems;
+    out[5] = pl.ptS0; out[6] = pl.n_split; out[7] = (int64_t)pl.partial_doubles;
+    for (int i = 0; i < pl.nph; ++i) {
+        int64_t *o = out + 8 + 5 * i;
+        o[0] = pl.ph[i].idx0; o[1] = pl.ph[i].S; o[2] = pl.ph[i].cps; o[3] = pl.ph[i].pt0;
+        o[4] = pl.ph[i].part0;
+    }
     return RVL_OK;
 }
 

@@ -156,11 +156,21 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
                    int64_t n_table_doubles);
 /* knobs, by name; unknown name -> RVL_EINVAL:
  *   "timing"    1: record CUDA events around the likelihood kernel (rvl_last_kernel_ms); default 0
- *   "zero_copy" 1 (default): host-buffer calls whose buffers are page-locked (pinned) are served in
- *               place -- the kernels read theta/U and write theta/lnL over PCIe, no staging copies
+ *   "zero_copy" host-buffer calls whose buffers are page-locked (pinned): 1 (default) lnL / theta
+ *               outputs and the U input of the fused call are served in place over PCIe, theta of
+ *               rvl_loglike is staged by one DMA copy; 2 also reads that theta in place (through
+ *               the once-per-point pass); 0 stages everything
  *   "variant"   0 optimised kernel (default), 1 conservative cross-check (IEEE division, full sin/cos)
  *   "ilp"       epochs per lane in flight, 1 or 2 (default 2)
- *   "slices", "warps", "min_chunks", "items_per_warp": launch-plan overrides (0 = automatic) */
+ *   "sched"     1 (default): graded work list -- whole points first, then the points at the end of the
+ *               batch cut into 2, 4, .. "max_split" (8) sub-slices with about "phase_items" (200)
+ *               percent of one item per warp in each phase, so that all warps run dry together;
+ *               0: one uniform slice count ("items_per_warp", "min_chunks")
+ *   "setup_items" 1 (default): the constants of the points that are cut into several items are
+ *               derived once, by setup items at the head of the kernel's own work list
+ *   "prepare"   1: per-point constants from the once-per-point pass even without a transform
+ *   "trace"     1: per-warp time stamps of the last launch (rvl_read_trace)
+ *   "slices", "warps": launch-plan overrides (0 = automatic) */
 int rvl_set_option(rvl_t *h, const char *name, int64_t value);
 
 /* ---- hot path: host buffers, synchronous -------------------------------- */
@@ -203,6 +213,16 @@ int rvl_last_kernel_ms(rvl_t *h, double *ms);
 int rvl_launch_count(rvl_t *h, uint64_t *n);
 /* register-resident DFMA loop: measured FP64 peak of this device, TFLOP/s (2 flop per DFMA) */
 int rvl_fp64_peak(rvl_t *h, double *tflops);
+/* option "trace" = 1: every warp of the likelihood kernel records { t_enter, t_ready (epoch data
+ * resident), t_done } in ns of the device's global timer and its number of work items; this
+ * reads the rows of the last launch (tools/warp_trace.py draws the drain curve from them). */
+int rvl_read_trace(rvl_t *h, uint64_t *out, int32_t cap_rows, int32_t *rows);
+/* The launch plan as data (no device needed; tests/test_plan.py checks that the work items cover
+ * every (point, epoch chunk) exactly once).  in[13] = { Npad/32, ncol, wstride, ilp, warps,
+ * sm_count, smem_optin, sched, slices, items_per_warp, min_chunks, phase_items, max_split };
+ * out[0..8) = { Sm, cpm, grid, n_phases, items per queue, first split point, split points,
+ * partial-sum doubles }, then per phase { idx0, S, cps, pt0, part0 }. */
+int rvl_plan_describe(const int32_t *in, int64_t B, int64_t *out, int32_t cap);
 /* sm count, smem per block opt-in, clock (kHz) */
 int rvl_device_info(rvl_t *h, int32_t *sm_count, int32_t *smem_optin, int32_t *clock_khz);
 

@@ -77,6 +77,50 @@ def test_slicing_is_consistent_and_deterministic(models, name):
     m.set_option("slices", 0)
 
 
+@pytest.mark.parametrize("cfg,B", [(2, 4096), (2, 300), (1, 5000), (5, 700)])
+def test_graded_work_list_vs_uniform_and_oracle(cfg, B):
+    """The graded work list (whole points first, the batch's last points cut into 2..16 items that
+    the last-arriving item adds up) against one-item-per-point launches and the C oracle; repeated
+    launches re-use the self-resetting work / arrival counters."""
+    import torch
+    from evidence_b200 import synth
+    from evidence_b200.rvmodel import RVModel
+    from oracle import rv_oracle
+    case = synth.make_case(cfg)
+    m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
+    theta = case.draw_theta(B, seed=40 + cfg)
+    theta[B // 2, case.parnames.index("planet1_ecc")] = 0.5
+    t, v, s, ids = case.arrays()
+    want, _, _ = rv_oracle.c_loglike_batch(m.desc_bytes(), t, v, s, ids.astype(np.int32),
+                                           len(case.insts), theta)
+    m.reset_counters()
+    graded = m.log_likelihood_batch(theta)
+    c = m.counters()
+    assert c["n_solves"] == B * case.n_epochs * case.n_planets and c["n_points"] == B
+    ok, worst = lnl_close(graded, want)
+    assert ok, worst
+    for _ in range(3):
+        assert np.array_equal(m.log_likelihood_batch(theta), graded)
+    for opts in ({"sched": 0}, {"slices": 1}, {"phase_items": 300, "max_split": 8},
+                 {"phase_items": 30, "max_split": 64}, {"prepare": 1}):
+        for k, val in opts.items():
+            m.set_option(k, val)
+        got = m.log_likelihood_batch(theta)
+        assert np.max(np.abs(got - graded)) <= 5e-10, opts
+        for k in opts:
+            m.set_option(k, {"sched": 1, "slices": 0, "phase_items": 100, "max_split": 16,
+                             "prepare": 0}[k])
+    # other batch sizes on the same handle (new plans over the same counters), then the first again
+    for b2 in (1, 33, B // 3):
+        ok, worst = lnl_close(m.log_likelihood_batch(theta[:b2]), want[:b2])
+        assert ok, (b2, worst)
+    assert np.array_equal(m.log_likelihood_batch(theta), graded)
+    dev = m.log_likelihood_device(torch.from_numpy(theta).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), graded)
+    m.close()
+
+
 def test_mixed_parametrisations_and_invalid_rows(models):
     meta, z, m = models("edge_mixed")
     theta, want = z["theta"], z["lnl"]
@@ -156,7 +200,10 @@ def test_full_size_properties():
     assert np.all(np.isfinite(a)) and np.all(a < 0)
     perm = np.random.default_rng(0).permutation(B)
     b = m.log_likelihood_batch(theta[perm])
-    assert np.array_equal(b, a[perm])  # a row's lnL does not depend on its position or neighbours
+    # a row's lnL does not depend on its neighbours; its position only picks the summation tree
+    # (the rows at the end of a batch are cut into finer work items): last-bits differences
+    assert np.max(np.abs(b - a[perm])) <= 5e-10
+    assert np.array_equal(b, m.log_likelihood_batch(theta[perm]))  # deterministic
     c = np.concatenate([m.log_likelihood_batch(theta[:B // 3]), m.log_likelihood_batch(theta[B // 3:])])
     assert np.max(np.abs(c - a)) <= 5e-10  # batch split (may pick another slice count)
     # raising every jitter can only lower the chi^2 term and raise the log-det term: check the
