@@ -20,6 +20,7 @@ solver from oracle/_ref) on the box's host cores.
 `--impl reference` times that CPU implementation alone, on the same config/metric.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -329,7 +330,6 @@ def main():
             kms.append(model.last_kernel_ms())
     barrier()
     t_wall = time.perf_counter() - t_wall
-    clk = clocks.stop()
     dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     launches = model.launch_count() - launches0
     if not inner_events:
@@ -357,11 +357,20 @@ def main():
     for _ in range(W):
         e2e_step()
     barrier()
+    # a full collection of the interpreter's heap (torch, numpy, ... imported) takes ~45 ms and
+    # would land inside this wall-clock region: collect now, keep the collector off while timing
+    gc.collect()
+    gc.disable()
     t0 = time.perf_counter()
+    marks = [t0]
     for k in range(K):
         e2e_step()
+        marks.append(time.perf_counter())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
+    e2e_us = np.diff(np.array(marks)) * 1e6  # per call (every call ends with a stream sync)
+    clk = clocks.stop()  # the sampler covers both timed regions
 
     if world > 1:
         red = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -388,7 +397,9 @@ def main():
         "config": dict(workload_config(case, B, world), gather=gather),
         "clocks": clk,
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": int(B * case.ndim * 8), "d2h_bytes_per_step": int(B * 8)},
+                "h2d_bytes_per_step": int(B * case.ndim * 8), "d2h_bytes_per_step": int(B * 8),
+                "us_per_call_percentiles_1_50_99": [float(x) for x in np.percentile(e2e_us, [1, 50, 99])],
+                "us_per_call_max": float(e2e_us.max())},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,

@@ -82,7 +82,8 @@ struct KArgs {
     double *gconsts;  // [n_setup][wstride] constants of the split points, written by the setup items
     unsigned *ready;  // [n_setup] seq*2 + invalid once the constants of the point are in gconsts
     int nph;
-    int wstride;     // doubles per warp in the constant block
+    int wstride;     // doubles of per-point constants
+    int wblock;      // doubles per warp in shared memory: the constants + a staged theta row
     Phase ph[kMaxPhases];
     PeerOut peers;
     unsigned long long *trace;  // optional [grid*warps][4]: t_enter, t_ready, t_done (ns), items
@@ -578,7 +579,15 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     for (int i = 1; i < 4; ++i)
         if (m.drift[i].slot >= 0 || m.drift[i].value != 0.0) drift_hi = i;
     const int nlin = m.n_linpar;
-    double *wc = wconst + (size_t)warp * a.wstride;
+    double *wc = wconst + (size_t)warp * a.wblock;
+    double *srow = wc + a.wstride;  // the point's theta row, staged by one coalesced read
+    // (theta may live in pinned host memory -- zero-copy calls -- where the scattered 8-byte
+    // reads of point_setup would each be a PCIe transaction)
+    auto stage_row = [&](const double *g) {
+        __syncwarp();
+        for (int i = lane; i < m.ndim; i += 32) srow[i] = g[i];
+        __syncwarp();
+    };
     // 32-bit shared-window addresses of everything the hot loop reads
     const uint32_t a_wc = smem_u32(wc);
     const uint32_t a_ic = a_wc + (uint32_t)(K * kPlanetStride) * 8u;
@@ -616,8 +625,8 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
         unsigned next = 0;
         if (lane == 0) next = atomicAdd(&a.work[sl], 1u);
         const long long pt = a.ptS0 + (long long)idx;
-        const bool valid =
-            point_setup(m, a.theta + pt * m.ndim, a.gconsts + (size_t)idx * a.wstride, lane);
+        stage_row(a.theta + pt * m.ndim);
+        const bool valid = point_setup(m, srow, a.gconsts + (size_t)idx * a.wstride, lane);
         __threadfence();
         __syncwarp();
         if (lane == 0) st_release_u32(a.ready + idx, a.seq * 2u + (valid ? 0u : 1u));
@@ -664,7 +673,8 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
             // must stay under uniform control flow)
             valid = __all_sync(kFull, (pf_flag & 1u) == 0u);
         } else {
-            valid = point_setup(m, row, wc, lane);
+            stage_row(row);
+            valid = point_setup(m, srow, wc, lane);
         }
         // what the rest of this iteration needs of the current item (the item variables are
         // re-used for the next one before the reduction)
@@ -1158,7 +1168,7 @@ int ensure_partial(rvl_t *h, long long B, size_t partial_doubles, long long n_sp
 }
 
 struct Plan {
-    int Sm, cpm, W, U, grid, wstride;
+    int Sm, cpm, W, U, grid, wstride, wblock;
     size_t smem;
     int nph;
     Phase ph[kMaxPhases];
@@ -1179,7 +1189,7 @@ size_t smem_need(int ncol, int ne, int W, int wstride)
 // phase holding about one item per warp: the work handed out last is the finest, so all warps of
 // the chip run dry together (a batch of ndraw = 4096 points is ONE point per warp otherwise).
 struct PlanIn {
-    int Ctot, ncol, wstride, U, W, sm_count, smem_optin;
+    int Ctot, ncol, wstride, wblock, U, W, sm_count, smem_optin;
     int sched, slices, items_per_warp, min_chunks, phase_items, max_split;
 };
 
@@ -1190,7 +1200,7 @@ const char *plan_core(const PlanIn &in, long long B, Plan &pl)
     int Sm = 1, cpm = 0;
     auto cpm_of = [&](int s) { return ((Ctot + s - 1) / s + U - 1) / U * U; };  // whole U-chunk trips
     auto fits = [&](int s) {
-        return smem_need(h->ncol, cpm_of(s) * 32, W, wstride) <= (size_t)h->smem_optin;
+        return smem_need(h->ncol, cpm_of(s) * 32, W, in.wblock) <= (size_t)h->smem_optin;
     };
     while (Sm < Ctot && Sm < h->sm_count && !fits(Sm)) ++Sm;
     if (!fits(Sm)) return "epoch range does not fit in shared memory";
@@ -1198,7 +1208,8 @@ const char *plan_core(const PlanIn &in, long long B, Plan &pl)
     Sm = (Ctot + cpm - 1) / cpm;  // drop empty trailing ranges
     pl.Sm = Sm; pl.cpm = cpm; pl.W = W; pl.U = U; pl.wstride = wstride;
     pl.grid = std::max(1, h->sm_count / Sm) * Sm;
-    pl.smem = smem_need(h->ncol, cpm * 32, W, wstride);
+    pl.smem = smem_need(h->ncol, cpm * 32, W, in.wblock);
+    pl.wblock = in.wblock;
 
     // sub-slice counts available within one resident range: S -> cps = ceil(cpm / S) in whole trips
     auto cps_of = [&](int S) { return ((cpm + S - 1) / S + U - 1) / U * U; };
@@ -1269,6 +1280,7 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     in.Ctot = h->Npad / 32;
     in.ncol = h->ncol;
     in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1) & ~1;
+    in.wblock = in.wstride + ((m.ndim + 1) & ~1);
     in.U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
     in.W = std::max(1, std::min(32, h->opt_warps > 0 ? h->opt_warps : (in.U == 2 ? 28 : 32)));
     in.sm_count = h->sm_count; in.smem_optin = h->smem_optin;
@@ -1346,7 +1358,7 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     a.consts = prepare ? h->d_consts : nullptr;
     a.B = B; a.ptS0 = pl.ptS0; a.cte = -0.5 * h->N * log(2 * M_PI); a.N = h->N; a.Npad = h->Npad;
     a.ncol = h->ncol; a.Sm = pl.Sm; a.cpm = pl.cpm; a.nitems = pl.nitems; a.nph = pl.nph;
-    a.wstride = pl.wstride;
+    a.wstride = pl.wstride; a.wblock = pl.wblock;
     for (int i = 0; i < pl.nph; ++i) a.ph[i] = pl.ph[i];
     if (peers) a.peers = *peers;
     if (h->opt_trace) {
@@ -1645,14 +1657,21 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
     DevGuard g(h->device);
     int rc = ensure_io(h, B);
     if (rc) return rc;
-    // A pinned theta is read in place (zero-copy) by the once-per-point prepare pass: one
-    // coalesced read per row over PCIe, constants left in HBM for the likelihood kernel (whose
-    // own per-item setup would read the row several times).  Pageable theta is staged by a copy.
-    // A pinned lnL is written in place.
+    // A pinned theta is read in place (zero-copy): the likelihood kernel reads every row ONCE, with
+    // one coalesced warp read (the setup item of a split point, or the point's only item), so the
+    // PCIe transfer overlaps the arithmetic instead of preceding it.  When the epoch axis needs
+    // several resident ranges every range would read the row: theta is then staged by a copy, as
+    // pageable theta always is.  A pinned lnL is written in place.
     const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
-    double *th_dev = h->opt_zero_copy > 1 ? (double *)pinned_alias(h, Theta) : nullptr;
+    Plan pl;
+    if (h->cols_dirty) { rc = upload_columns(h); if (rc) return rc; }
+    rc = make_plan(h, B, pl);
+    if (rc) return rc;
+    const bool once = pl.Sm == 1 && (h->opt_setup_items || pl.n_split == 0) && !h->opt_prepare;
+    double *th_dev = (h->opt_zero_copy > 1 || (h->opt_zero_copy == 1 && once))
+                         ? (double *)pinned_alias(h, Theta) : nullptr;
     double *out_dev = (double *)pinned_alias(h, lnL);
-    const bool via_prepare = th_dev != nullptr;
+    const bool via_prepare = th_dev != nullptr && !once;
     if (!th_dev) {
         th_dev = h->d_theta;
         if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
@@ -1829,7 +1848,7 @@ int rvl_plan_describe(const int32_t *in, int64_t B, int64_t *out, int32_t cap)
 {
     if (!in || !out || cap < 8) return RVL_EINVAL;
     PlanIn pi{};
-    pi.Ctot = in[0]; pi.ncol = in[1]; pi.wstride = in[2]; pi.U = in[3]; pi.W = in[4];
+    pi.Ctot = in[0]; pi.ncol = in[1]; pi.wstride = in[2]; pi.wblock = in[2]; pi.U = in[3]; pi.W = in[4];
     pi.sm_count = in[5]; pi.smem_optin = in[6]; pi.sched = in[7]; pi.slices = in[8];
     pi.items_per_warp = in[9]; pi.min_chunks = in[10]; pi.phase_items = in[11]; pi.max_split = in[12];
     if (pi.Ctot < 1 || pi.U < 1 || pi.U > 2 || pi.W < 1 || pi.sm_count < 1 || B < 1) return RVL_EINVAL;

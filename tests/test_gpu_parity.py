@@ -108,7 +108,7 @@ def test_graded_work_list_vs_uniform_and_oracle(cfg, B):
         got = m.log_likelihood_batch(theta)
         assert np.max(np.abs(got - graded)) <= 5e-10, opts
         for k in opts:
-            m.set_option(k, {"sched": 1, "slices": 0, "phase_items": 100, "max_split": 16,
+            m.set_option(k, {"sched": 1, "slices": 0, "phase_items": 200, "max_split": 8,
                              "prepare": 0}[k])
     # other batch sizes on the same handle (new plans over the same counters), then the first again
     for b2 in (1, 33, B // 3):
