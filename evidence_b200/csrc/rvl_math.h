@@ -260,37 +260,10 @@ constexpr double kSmallStep = 0x1p-5;
 // Given E with (s, c) = (sin E, cos E):  f = (E - ec s) - M  [two grid roundings, as the
 // reference], f' = 1 - ec c, E_new = E - f * rcp(f') [one grid rounding].  Returns E_new - E,
 // which is exact (Sterbenz) and is the quantity the reference thresholds against tol (:21).
-#ifndef RVL_F_FMA
-#define RVL_F_FMA 0  // 1: E - ec s with one rounding (FMA) instead of the reference's two
-#endif
-RVL_HD double rcp1(double x)  // one Newton refinement: relative error ~2^-40
-{
-    double y;
-#if defined(__CUDA_ARCH__)
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#else
-    {  // host stand-in with the hardware's ~20-bit seed accuracy
-        float f = 1.0f / (float)x;
-        uint32_t u;
-        memcpy(&u, &f, 4);
-        u &= 0xfffffff0u;
-        memcpy(&f, &u, 4);
-        y = (double)f;
-    }
-#endif
-    const double e = fma_(-x, y, 1.0);
-    return fma_(y, e, y);
-}
-template <bool PRECISE = true>
 RVL_HD double newton_step(double E, double s, double c, double M, double ec, double &Enew)
 {
-    const double den = fma_(-ec, c, 1.0);
-    const double r = PRECISE ? rcp(den) : rcp1(den);
-#if RVL_F_FMA
-    const double f = sub(fma_(-ec, s, E), M);
-#else
+    const double r = rcp(fma_(-ec, c, 1.0));
     const double f = sub(sub(E, mul(ec, s)), M);
-#endif
     Enew = fma_(-f, r, E);
     return sub(Enew, E);
 }

@@ -64,8 +64,6 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
                 all_medium = all_medium && (h < kHiMedium);
                 any_big = any_big || !(abs_hi(E[u][l]) < kHiTrigMax);
             }
-        const bool coarse = !(all_tiny || all_small);  // the step that follows a full/medium pass
-        (void)coarse;
         if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(d[u][l], s[u][l], c[u][l]); }
         else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(d[u][l], s[u][l], c[u][l]); }
         else if (!slow && all_medium) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_medium(d[u][l], s[u][l], c[u][l]); }
@@ -89,10 +87,6 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
         for (int u = 0; u < U; ++u)
             for (int l = 0; l < W; ++l) {
                 double En;
-#ifdef RVL_EMUL_RCP1
-                if (coarse) rvl::newton_step<false>(E[u][l], s[u][l], c[u][l], M[u][l], ec, En);
-                else
-#endif
                 rvl::newton_step(E[u][l], s[u][l], c[u][l], M[u][l], ec, En);
                 En = pa[u][l] ? En : E[u][l];
                 d[u][l] = En - E[u][l];
