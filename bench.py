@@ -238,9 +238,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline and sweeps")
-    ap.add_argument("--gather", default="nccl", choices=["fused", "nccl"],
-                    help="multi-GPU: NCCL all_gather (default) or the all-gather fused into the "
-                         "producing kernel over NVLink symmetric memory")
+    ap.add_argument("--gather", default="fused", choices=["fused", "fused-barrier", "nccl"],
+                    help="multi-GPU: the all-gather fused into the likelihood launch over NVLink "
+                         "symmetric memory (peer stores + completion flags; default), the same with "
+                         "a symmetric-memory barrier, or NCCL all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -287,11 +288,13 @@ def main():
     lnl = torch.empty(B, dtype=torch.float64, device="cuda")
     sharded = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk, out=lnl), case.ndim)
     gather = "none" if world == 1 else "nccl all_gather"
-    if world > 1 and args.gather == "fused":
+    if world > 1 and args.gather != "nccl":
         try:  # all-gather fused into the producing kernel over NVLink symmetric memory
             from evidence_b200.multigpu import FusedGatherLikelihood
-            sharded = FusedGatherLikelihood(model, B)
-            gather = "fused into the kernel (peer stores over NVLink symmetric memory + signal barrier)"
+            sig = "flags" if args.gather == "fused" else "barrier"
+            sharded = FusedGatherLikelihood(model, B, signal=sig)
+            gather = ("fused into the likelihood launch (peer stores over NVLink symmetric memory + "
+                      + ("completion flags)" if sig == "flags" else "symmetric-memory barrier)"))
         except Exception as exc:  # symmetric memory unavailable: NCCL all-gather
             print(f"fused gather unavailable ({exc!r}); using NCCL all_gather", file=sys.stderr)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

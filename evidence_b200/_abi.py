@@ -77,6 +77,8 @@ SYMBOLS = {
     "rvl_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "rvl_loglike_dev_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),
                                           c_int32, c_int64, c_void_p]),
+    "rvl_loglike_dev_gather": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),
+                                         c_int32, c_int32, c_int64, c_int64, c_uint64, c_void_p]),
     "rvl_transform_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                             c_void_p]),
     "rvl_trueanomaly": (c_int32, [c_void_p, _dp, c_int32, c_double, _dp, c_int32, c_double]),

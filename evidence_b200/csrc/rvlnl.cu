@@ -45,6 +45,12 @@ struct PeerOut {
     double *ptr[RVL_MAX_PEERS];
     int n;
     long long offset;  // element offset of this rank's block inside every gathered vector
+    // completion signal (seq != 0): when the whole launch is done, slot flag_off + rank of every
+    // peer buffer receives seq (64-bit, release at system scope) -- the consumer side waits for
+    // all ranks' slots of its own buffer instead of running a barrier or a collective
+    long long flag_off;
+    unsigned long long seq;
+    int rank;
 };
 
 // One phase of the work list of a queue.  Items idx0 .. (next phase's idx0 - 1) cover points
@@ -816,9 +822,33 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     // the last block to leave re-arms the work counters for the next launch on this handle
     __syncthreads();
     if (tid == 0) {
-        __threadfence();
+        if (a.peers.n) __threadfence_system(); else __threadfence();
         if (atomicAdd(&a.work[a.Sm], 1u) == gridDim.x - 1) {
             for (int i = 0; i <= a.Sm; ++i) a.work[i] = 0u;
+            if (a.peers.seq) {
+                // every block's peer stores are ordered (system-scope fence) before its arrival
+                // above, which this thread has observed: the release stores below publish them
+                for (int r = 0; r < a.peers.n; ++r) {
+                    unsigned long long *f = reinterpret_cast<unsigned long long *>(a.peers.ptr[r]) +
+                                            a.peers.flag_off + a.peers.rank;
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.peers.seq)
+                                 : "memory");
+                }
+            }
+        }
+    }
+}
+
+// consumer side of the fused all-gather: returns once every rank's completion slot holds >= seq
+__global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long seq)
+{
+    if ((int)threadIdx.x < n) {
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x)
+                         : "memory");
+            if (v >= seq) break;
+            __nanosleep(64);
         }
     }
 }
@@ -1627,6 +1657,33 @@ int rvl_loglike_dev_scatter(rvl_t *h, const double *dTheta, int64_t B, double *d
     DevGuard g(h->device);
     return enqueue_loglike(h, nullptr, const_cast<double *>(dTheta), B, dlnL, (cudaStream_t)stream,
                            h->opt_timing != 0, &po);
+}
+
+int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dlnL,
+                           const uint64_t *peer_ptrs, int32_t n_peers, int32_t rank, int64_t offset,
+                           int64_t flag_offset, uint64_t seq, void *stream)
+{
+    if (!h) return RVL_EINVAL;
+    if (B <= 0 || !dTheta || !dlnL) return fail(h, RVL_EINVAL, "bad arguments");
+    if (n_peers < 1 || n_peers > RVL_MAX_PEERS || !peer_ptrs || offset < 0 || rank < 0 ||
+        rank >= n_peers || flag_offset < 0 || seq == 0)
+        return fail(h, RVL_EINVAL, "bad peer list");
+    PeerOut po{};
+    po.n = n_peers;
+    po.offset = offset;
+    po.flag_off = flag_offset;
+    po.seq = seq;
+    po.rank = rank;
+    for (int r = 0; r < n_peers; ++r) po.ptr[r] = reinterpret_cast<double *>(peer_ptrs[r]);
+    DevGuard g(h->device);
+    int rc = enqueue_loglike(h, nullptr, const_cast<double *>(dTheta), B, dlnL, (cudaStream_t)stream,
+                             h->opt_timing != 0, &po);
+    if (rc) return rc;
+    wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long *>(po.ptr[rank]) + flag_offset, n_peers, seq);
+    CU(h, cudaGetLastError());
+    ++h->launches;
+    return RVL_OK;
 }
 
 int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream)

@@ -11,11 +11,12 @@ counts on every rank.
 Two ways to do the gather:
 
 * ``ShardedLikelihood`` -- the likelihood kernel, then ``all_gather_into_tensor`` (NCCL).
-* ``FusedGatherLikelihood`` -- the all-gather is fused into the producing kernel: the kernel that
-  finishes lnL stores each value straight into every rank's gathered vector through NVLink
-  peer-mapped (symmetric) memory (``rvl_loglike_dev_scatter``), and the ranks then meet at one
-  signal barrier.  No collective launch, no staging copy; saves the latency of a separate
-  all-gather on these 4 KB - 10 MB messages.
+* ``FusedGatherLikelihood`` -- the all-gather is fused into the producing kernel: the work item
+  that finishes a point's lnL stores it straight into every rank's gathered vector through
+  NVLink peer-mapped (symmetric) memory, and the launch's last block then stores a sequence
+  number into a completion slot of every peer buffer; each rank waits (one warp, stream-ordered)
+  for the slots of its own buffer (``rvl_loglike_dev_gather``).  No collective, no barrier, no
+  staging copy on these 4 KB - 10 MB messages.
 """
 import math
 
@@ -86,25 +87,39 @@ class FusedGatherLikelihood:
     docstring).  Every rank calls ``evaluate_local(theta_block)`` with its own block of the same
     row count and receives the gathered ``lnL[world * rows]`` (a view into symmetric memory that
     stays valid until the call after next: two buffers alternate).
+
+    ``signal="flags"`` (default): the launch itself tells the peers when it is done -- its last
+    block stores a sequence number into a completion slot of every peer buffer, and a one-warp
+    kernel behind it waits for all ranks' slots (``rvl_loglike_dev_gather``).
+    ``signal="barrier"``: peer stores, then torch's symmetric-memory barrier.
     """
 
-    def __init__(self, model, max_rows, group=None):
+    def __init__(self, model, max_rows, group=None, signal="flags"):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
+        if signal not in ("flags", "barrier"):
+            raise ValueError("signal must be 'flags' or 'barrier'")
         self.model = model
+        self.signal = signal
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.max_rows = int(max_rows)
         grp = group if group is not None else dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.bufs, self.hdls, self.ptrs = [], [], []
+        self.bufs, self.hdls, self.ptrs, self.seq = [], [], [], []
+        self.flag_off = self.world * self.max_rows  # completion slots follow the gathered vector
         for _ in range(2):
-            buf = symm.empty(self.world * self.max_rows, dtype=torch.float64, device=dev)
+            buf = symm.empty(self.flag_off + self.world, dtype=torch.float64, device=dev)
             hdl = symm.rendezvous(buf, grp)
+            buf.zero_()
             self.bufs.append(buf)
             self.hdls.append(hdl)
             self.ptrs.append([int(p) for p in hdl.buffer_ptrs])
+            self.seq.append(0)
+        torch.cuda.synchronize()
+        for hdl in self.hdls:
+            hdl.barrier()  # every rank's slots are zero before anybody signals
         self.local = torch.empty(self.max_rows, dtype=torch.float64, device=dev)
         self.turn = 0
 
@@ -115,7 +130,13 @@ class FusedGatherLikelihood:
         k = self.turn
         self.turn ^= 1
         # every lnL value is written into all ranks' buffer k at [rank*rows + i] by the kernel
-        self.model.log_likelihood_device_scatter(theta_block, self.local[:rows], self.ptrs[k],
-                                                 self.rank * rows)
-        self.hdls[k].barrier()  # all peers' stores have landed
+        if self.signal == "flags":
+            self.seq[k] += 1
+            self.model.log_likelihood_device_gather(theta_block, self.local[:rows], self.ptrs[k],
+                                                    self.rank, self.rank * rows, self.flag_off,
+                                                    self.seq[k])
+        else:
+            self.model.log_likelihood_device_scatter(theta_block, self.local[:rows], self.ptrs[k],
+                                                     self.rank * rows)
+            self.hdls[k].barrier()  # all peers' stores have landed
         return self.bufs[k][: self.world * rows]

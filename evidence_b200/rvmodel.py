@@ -217,6 +217,24 @@ class RVModel(BaseModel):
             int(offset), c_void_p(stream)))
         return out
 
+    def log_likelihood_device_gather(self, theta, out, peer_ptrs, rank, offset, flag_offset, seq):
+        """
+        The all-gather inside the likelihood launch (``rvl_loglike_dev_gather``): lnL goes into every
+        peer buffer at element ``offset``, the finished launch stores ``seq`` into completion slot
+        ``flag_offset + rank`` of every peer buffer, and a one-warp kernel behind it waits for all
+        ranks' slots of this rank's own buffer.  Stream-ordered; no barrier, no collective.
+        """
+        import torch
+        if not (theta.is_cuda and theta.dtype == torch.float64 and theta.is_contiguous()):
+            raise ValueError("theta must be a contiguous CUDA float64 tensor")
+        B = theta.shape[0]
+        arr = (c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        stream = torch.cuda.current_stream(theta.device).cuda_stream
+        self._check(self._lib.rvl_loglike_dev_gather(
+            self._h, c_void_p(theta.data_ptr()), B, c_void_p(out.data_ptr()), arr, len(peer_ptrs),
+            int(rank), int(offset), int(flag_offset), int(seq), c_void_p(stream)))
+        return out
+
     # ------------------------------------------------------------------ priors
     def set_priors(self, priordict):
         """

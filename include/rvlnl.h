@@ -198,6 +198,18 @@ int rvl_loglike_dev_scatter(rvl_t *h, const double *dTheta, int64_t B, double *d
                             const uint64_t *peer_ptrs, int32_t n_peers, int64_t offset,
                             void *stream);
 
+/* The whole all-gather inside the likelihood launch.  As rvl_loglike_dev_scatter, and when the
+ * launch has finished its last work item it stores `seq` (64-bit, release, system scope) into slot
+ * `flag_offset + rank` (in 8-byte elements) of EVERY peer buffer; a one-warp kernel enqueued behind
+ * it on `stream` then waits until all n_peers slots of this rank's own buffer (peer_ptrs[rank])
+ * hold >= seq.  When that returns -- in stream order -- the gathered vector is complete on this
+ * rank: no barrier, no collective.  The caller zeroes the slots once, uses seq = 1, 2, 3, ... per
+ * buffer, and alternates two buffers so that a fast rank never overwrites what a slow one still
+ * reads (evidence_b200/multigpu.py: FusedGatherLikelihood). */
+int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dlnL,
+                           const uint64_t *peer_ptrs, int32_t n_peers, int32_t rank, int64_t offset,
+                           int64_t flag_offset, uint64_t seq, void *stream);
+
 /* ---- the reference's own native FFI, on the device (trueanomaly.h:4) ----- */
 /* Same contract as the reference symbol except: returns -1 when ANY element hit the cap
  * (every nu[i] is still written from the last iterate, the reference leaves the rest 0). */

@@ -34,11 +34,18 @@ def _worker(rank, world, port, ret):
         rows = 1000
         theta = torch.from_numpy(case.draw_theta(rows, seed=50 + rank)).cuda()
         nccl = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk), case.ndim)
-        fused = FusedGatherLikelihood(model, rows)
         want = nccl.evaluate_local(theta).cpu().numpy()
         outs = []
-        for _ in range(3):  # alternating buffers
-            outs.append(fused.evaluate_local(theta).clone())
+        for signal in ("flags", "barrier"):
+            fused = FusedGatherLikelihood(model, rows, signal=signal)
+            for _ in range(5):  # alternating buffers
+                outs.append(fused.evaluate_local(theta).clone())
+            # a smaller block through the same buffers
+            part = fused.evaluate_local(theta[:333].contiguous()).clone()
+            # (another batch size picks another summation tree: last-bits differences)
+            assert torch.allclose(part[rank * 333:(rank + 1) * 333],
+                                  torch.from_numpy(want[rank * rows:rank * rows + 333]).cuda(),
+                                  rtol=0.0, atol=5e-10)
         torch.cuda.synchronize()
         ret[rank] = (want, [o.cpu().numpy() for o in outs])
         model.close()
