@@ -286,13 +286,15 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
             double En;
             if (VARIANT == 0) {
                 rvl::newton_step(E[u], s[u], c[u], M[u], ec, En);
+                En = pa[u] ? En : E[u];
+                d[u] = rvl::sub(En, E[u]);  // exact
             } else {
                 const double f = rvl::sub(rvl::sub(E[u], rvl::mul(ec, s[u])), M[u]);
                 const double fp = rvl::sub(1.0, rvl::mul(ec, c[u]));
                 En = rvl::sub(E[u], __ddiv_rn(f, fp));
+                En = pa[u] ? En : E[u];
+                d[u] = rvl::sub(En, E[u]);  // exact
             }
-            En = pa[u] ? En : E[u];
-            d[u] = rvl::sub(En, E[u]);  // exact
             E[u] = En;
             last[u] = pa[u] ? trip : last[u];
         }
@@ -597,7 +599,6 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     // 32-bit shared-window addresses of everything the hot loop reads
     const uint32_t a_wc = smem_u32(wc);
     const uint32_t a_ic = a_wc + (uint32_t)(K * kPlanetStride) * 8u;
-    const uint32_t a_dc = a_ic + (uint32_t)(2 * m.n_inst) * 8u;
     const uint32_t a_t = smem_u32(scol) + (uint32_t)lane * 8u;
     const uint32_t colb = (uint32_t)ne * 8u;  // bytes per column
     const uint32_t a_inst = smem_u32(sinst) + (uint32_t)lane;
