@@ -90,6 +90,9 @@ SYMBOLS = {
     "rvl_device_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32)]),
     "rvl_read_trace": (c_int32, [c_void_p, POINTER(c_uint64), c_int32, POINTER(c_int32)]),
+    "rvl_fip_accumulate": (c_int32, [c_int32, _dp, _dp, c_int32, _dp, c_int32, _dp, c_int64, c_double,
+                                     c_int32, c_double, c_double, _dp, _dp]),
+    "rvl_fip_last_error": (c_char_p, []),
     "rvl_plan_describe": (c_int32, [POINTER(c_int32), c_int64, POINTER(c_int64), c_int32]),
 }
 

@@ -47,6 +47,7 @@ extern "C" {
 #define RVL_MAX_LINPAR 8
 #define RVL_MAX_DIM 128
 #define RVL_MAX_PEERS 16
+#define RVL_FIP_MAX_PLANETS 8
 
 /* error codes */
 #define RVL_OK 0
@@ -238,6 +239,23 @@ int rvl_read_trace(rvl_t *h, uint64_t *out, int32_t cap_rows, int32_t *rows);
 int rvl_plan_describe(const int32_t *in, int64_t B, int64_t *out, int32_t cap);
 /* sm count, smem per block opt-in, clock (kHz) */
 int rvl_device_info(rvl_t *h, int32_t *sm_count, int32_t *smem_optin, int32_t *clock_khz);
+
+/* ---- next row of the path: FIP-periodogram accumulation ------------------ */
+/* Replaces the per-sample Python loop of evidence/fip_criterion.py:303-337 for ONE (run, k-planet
+ * model) block: for each of the n posterior samples (periods[n][k], days; weights[n], any positive
+ * normalisation) every grid bin j with nua[j] < f < ... -- precisely the bins
+ * range(searchsorted(nub, f, 'right'), searchsorted(nua, f, 'left')) of one of the sample's mean
+ * motions f = 2 pi / P (with_alias: also |f +- 2pi/0.99727|, |f +- 2pi/30|, kept when inside
+ * [2pi/pmax, 2pi/pmin]) -- receives  fapnu[j] -= pk * weight / sum(weights),  once per sample.
+ * nua / nub are the caller's arrays (fip_criterion.py:233-236), searched with the reference's own
+ * comparisons.  fapnu[nfreq] is updated in place (host buffer).  Accumulation is 2^-56 fixed point
+ * with integer atomics: bit-reproducible.  kernel_ms (optional): CUDA-event time of the two
+ * kernels.  No handle: device < 0 = current device.  Errors: rvl_fip_last_error(). */
+int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int32_t nfreq,
+                       const double *periods, int32_t k, const double *weights, int64_t n,
+                       double pk, int32_t with_alias, double pmin, double pmax, double *fapnu,
+                       double *kernel_ms);
+const char *rvl_fip_last_error(void);
 
 #ifdef __cplusplus
 }
