@@ -93,6 +93,9 @@ SYMBOLS = {
     "rvl_fip_accumulate": (c_int32, [c_int32, _dp, _dp, c_int32, _dp, c_int32, _dp, c_int64, c_double,
                                      c_int32, c_double, c_double, _dp, _dp]),
     "rvl_fip_last_error": (c_char_p, []),
+    "rvl_order_planets": (c_int32, [c_int32, _dp, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32),
+                                    c_int32, c_int32, _dp, _dp]),
+    "rvl_order_last_error": (c_char_p, []),
     "rvl_plan_describe": (c_int32, [POINTER(c_int32), c_int64, POINTER(c_int64), c_int32]),
 }
 

@@ -11,7 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "rvlnl.cu")
 SRC_FIP = os.path.join(_HERE, "csrc", "rvfip.cu")
-DEPS = [SRC, SRC_FIP, os.path.join(_HERE, "csrc", "rvl_math.h"),
+SRC_ORDER = os.path.join(_HERE, "csrc", "rvorder.cu")
+DEPS = [SRC, SRC_FIP, SRC_ORDER, os.path.join(_HERE, "csrc", "rvl_math.h"),
         os.path.join(os.path.dirname(_HERE), "include", "rvlnl.h")]
 OUT = os.path.join(_HERE, "librvlnl.so")
 
@@ -41,10 +42,10 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile evidence_b200/csrc/{rvlnl,rvfip}.cu -> evidence_b200/librvlnl.so for sm_100a."""
+    """Compile evidence_b200/csrc/{rvlnl,rvfip,rvorder}.cu -> evidence_b200/librvlnl.so for sm_100a."""
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, SRC_FIP]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, SRC_FIP, SRC_ORDER]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

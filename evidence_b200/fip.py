@@ -83,3 +83,43 @@ def fip_periodogram(runs, logZs, Pmin, Pmax, nfreq=50000, Tobs=1.0, coef_window=
             accumulate_block(fapnu[r], nua, nub, samples, weights, pky[kmod], Pmin, Pmax,
                              with_alias, device)
     return nu, fapnu
+
+
+# ------------------------------------------------------------------------------------------
+# posterior planet ordering (evidence/post_processing.py:93-128)
+def planet_tables(parnames, nplanets):
+    """The column lists the reference builds from the names (:94-102): planets[n-1] = columns
+    whose name contains 'planet{n}', planet_idxs = their 'period' columns."""
+    planets, planet_idxs = [], []
+    for n in range(1, nplanets + 1):
+        planets.append([i for i, par in enumerate(parnames) if f'planet{n}' in par])
+        planet_idxs += [i for i in planets[-1] if 'period' in parnames[i]]
+    return planets, planet_idxs
+
+
+def order_planets(samples, parnames, nplanets, device=-1):
+    """
+    The reference's ``order`` option of ``postprocess`` (evidence/post_processing.py:104-127) for a
+    whole posterior at once: rows whose planet periods are not non-decreasing get their planet
+    columns permuted exactly as the reference's index list does.  Returns a new array.
+    """
+    lib = _abi.load()
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    if samples.ndim != 2 or samples.shape[1] != len(parnames):
+        raise ValueError("samples must have one column per parameter name")
+    planets, planet_idxs = planet_tables(parnames, nplanets)
+    if nplanets < 1 or len(planet_idxs) != nplanets or len({len(p) for p in planets}) != 1:
+        raise ValueError("every planet needs one period column and the same number of parameters")
+    K, Q = nplanets, len(planets[0])
+    pc = (ctypes.c_int32 * K)(*planet_idxs)
+    cols = (ctypes.c_int32 * (K * Q))(*[c for p in planets for c in p])
+    out = np.empty_like(samples)
+    ms = ctypes.c_double(0.0)
+    rc = lib.rvl_order_planets(int(device), samples.ctypes.data_as(_dp), samples.shape[0],
+                               samples.shape[1], pc, cols, K, Q, out.ctypes.data_as(_dp),
+                               ctypes.byref(ms))
+    if rc != 0:
+        raise FIPError(f"librvlnl: {_abi.RVL_ERRORS.get(rc, rc)}: "
+                       f"{lib.rvl_order_last_error().decode()}")
+    order_planets.last_kernel_ms = ms.value
+    return out

@@ -48,6 +48,7 @@ extern "C" {
 #define RVL_MAX_DIM 128
 #define RVL_MAX_PEERS 16
 #define RVL_FIP_MAX_PLANETS 8
+#define RVL_ORDER_MAX_PARAMS 16
 
 /* error codes */
 #define RVL_OK 0
@@ -256,6 +257,19 @@ int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int
                        double pk, int32_t with_alias, double pmin, double pmax, double *fapnu,
                        double *kernel_ms);
 const char *rvl_fip_last_error(void);
+
+/* Replaces the posterior planet-ordering loop of evidence/post_processing.py:104-127: out[n][ndim]
+ * = samples[n][ndim] with, in every row whose K planet periods (columns period_cols[K]) are not
+ * non-decreasing, the columns of the planets (planet_cols[K][Q]: the Q columns of planet p, in
+ * parnames order -- :94-102) gathered through the reference's index list,
+ * new[planet_cols[p][q]] = old[planet_cols[rank(p)][q]] with rank = position of p in
+ * np.argsort(periods), exactly equal periods in planet order (numpy's default sort leaves ties
+ * platform-dependent), NaN last.  (That is the inverse of the sorting permutation; reproduced as is.)
+ * Host buffers; out must not alias samples.  Errors: rvl_order_last_error(). */
+int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t ndim,
+                      const int32_t *period_cols, const int32_t *planet_cols, int32_t K, int32_t Q,
+                      double *out, double *kernel_ms);
+const char *rvl_order_last_error(void);
 
 #ifdef __cplusplus
 }

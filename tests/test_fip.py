@@ -123,3 +123,50 @@ def test_no_cpu_fallback_without_a_gpu(built_lib):
     nu, nua, nub = fip.frequency_grid(1.0, 100.0, 100, 50.0)
     with pytest.raises(fip.FIPError, match="no CPU fallback"):
         fip.accumulate_block(np.ones(100), nua, nub, np.array([[10.0]]), np.array([1.0]), 1.0, 1.0, 100.0)
+
+
+# ------------------------------------------------------------------------ planet ordering
+def _posterior(seed, n, K, extra=("inst_jitter", "inst_offset", "drift_lin")):
+    rng = np.random.default_rng(seed)
+    names = list(extra)
+    for p in range(1, K + 1):
+        names += [f"planet{p}_{q}" for q in ("ecc", "k1", "ma0", "omega", "period")]
+    names = sorted(names)
+    s = rng.normal(size=(n, len(names)))
+    for p in range(1, K + 1):
+        s[:, names.index(f"planet{p}_period")] = np.exp(rng.uniform(0, 6, n))
+    return names, s
+
+
+def test_order_oracle_semantics():
+    """Two planets: a plain swap.  Three in cyclic disorder: the reference's gather applies the
+    INVERSE permutation (documented in oracle/order_oracle.py) -- pinned here as a known answer."""
+    from oracle.order_oracle import order_samples_literal
+    names = sorted(f"planet{p}_{q}" for p in (1, 2, 3) for q in ("k1", "period"))
+    row = np.array([[1.0, 30.0, 2.0, 10.0, 3.0, 20.0]])  # periods (30, 10, 20)
+    got = order_samples_literal(row, names, 3)
+    assert got.tolist() == [[3.0, 20.0, 1.0, 30.0, 2.0, 10.0]]
+    names2 = sorted(f"planet{p}_{q}" for p in (1, 2) for q in ("k1", "period"))
+    got2 = order_samples_literal(np.array([[1.0, 30.0, 2.0, 10.0], [1.0, 5.0, 2.0, 6.0]]), names2, 2)
+    assert got2.tolist() == [[2.0, 10.0, 1.0, 30.0], [1.0, 5.0, 2.0, 6.0]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [1, 2, 3, 5])
+def test_device_planet_ordering_vs_literal_reference_loop(K):
+    from evidence_b200 import fip
+    from oracle.order_oracle import order_samples_literal
+    names, s = _posterior(K, 3000, K)
+    s[5, names.index("planet1_period")] = np.nan            # NaN sorts last
+    if K > 1:
+        s[7, names.index("planet2_period")] = s[7, names.index("planet1_period")]  # a tie
+    want = order_samples_literal(s, names, K)
+    got = fip.order_planets(s, names, K)
+    rows = np.arange(len(s)) != 7
+    assert np.array_equal(got[rows], want[rows], equal_nan=True)   # byte movement: bit-exact
+    # exactly tied periods: numpy's default argsort is unstable (platform-dependent order), the
+    # device breaks the tie by planet index
+    want7 = order_samples_literal(s[7:8], names, K, kind="stable")
+    assert np.array_equal(got[7:8], want7, equal_nan=True)
+    assert np.array_equal(fip.order_planets(np.empty((0, len(names))), names, K),
+                          np.empty((0, len(names))))
