@@ -184,7 +184,9 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL);
 /* fused u -> theta -> lnL; Theta may be NULL when the sampler does not need it */
 int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, double *lnL);
 
-/* ---- hot path: device buffers, asynchronous on `stream` ------------------ */
+/* ---- hot path: device buffers, asynchronous on `stream` ------------------
+ * The launches of ONE handle share its work counters and scratch buffers: enqueue them in stream
+ * order (one stream at a time per handle; use one handle per stream for concurrency). */
 int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream);
 int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, void *stream);
 int rvl_transform_loglike_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta,
