@@ -230,6 +230,45 @@ def sweep(model_factory, case, batch, steps, torch, peak_tflops):
     return res
 
 
+def stress(model_factory, torch, peak_tflops, batch=10_000_000):
+    """BASELINE.json configs[4]: raw kernel stress, 1e7 parameter vectors x 1e4 epochs x 3 planets,
+    Kepler solves/s against the FP64 peak.  Everything stays on the device: U ~ torch.rand, the
+    prior transform fused in front of the likelihood (rvl_transform_loglike_dev)."""
+    from evidence_b200 import synth
+    case = synth.make_case(5)
+    model = model_factory(case)
+    model.set_priors(case.priordict)
+    model.set_option("timing", 1)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    U = torch.rand((100_000, case.ndim), dtype=torch.float64, device="cuda", generator=gen)
+    model.transform_loglike_device(U)  # warm launch
+    torch.cuda.synchronize()
+    U = torch.rand((batch, case.ndim), dtype=torch.float64, device="cuda", generator=gen)
+    theta = torch.empty_like(U)
+    lnl = torch.empty(batch, dtype=torch.float64, device="cuda")
+    model.reset_counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    model.transform_loglike_device(U, theta=theta, lnl=lnl)
+    e1.record()
+    torch.cuda.synchronize()
+    total_ms, k_ms = e0.elapsed_time(e1), model.last_kernel_ms()
+    c = model.counters()
+    mean_it = c["n_newton_iters"] / max(1, c["n_solves"])
+    F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
+    ach = batch * F / (k_ms * 1e-3) / 1e12
+    finite = bool(torch.isfinite(lnl).all().item())
+    res = {"workload": f"configs[4] stress: N={case.n_epochs} K={case.n_planets} batch={batch}, "
+                       "u -> theta -> lnL on the device",
+           "kepler_solves": int(c["n_solves"]), "kernel_ms": k_ms, "total_ms_with_prior_transform": total_ms,
+           "kepler_solves_per_s": c["n_solves"] / (k_ms * 1e-3), "lnl_per_s": batch / (k_ms * 1e-3),
+           "mean_newton_iters": mean_it, "achieved_tflops": ach,
+           "frac_of_fp64_peak": ach / peak_tflops if peak_tflops else None,
+           "newton_cap_hits": int(c["n_cap_hits"]), "all_finite": finite}
+    model.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,6 +463,7 @@ def main():
             sweeps.append(sweep(make_model, synth.make_case(3), 65536, 5, torch, peak))
             sweeps.append(sweep(make_model, synth.make_case(5), 32768, 3, torch, peak))
             line["sweeps"] = sweeps
+            line["stress"] = stress(make_model, torch, peak)
         except Exception as exc:  # extras must never cost the headline line
             line["sweeps_error"] = repr(exc)
         try:

@@ -223,6 +223,42 @@ def test_full_size_properties():
     m0.close()
 
 
+def test_config5_shape_at_scale_fused_transform():
+    """BASELINE configs[4] shape (N = 1e4, K = 3) at 1e6 points through the fused u -> theta -> lnL
+    device call; rows re-evaluated in small host batches must agree (bench.py runs the full 1e7)."""
+    import torch
+    from evidence_b200 import synth
+    from evidence_b200.rvmodel import RVModel
+    case = synth.make_case(5)
+    m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
+    m.set_priors(case.priordict)
+    B = 1_000_000
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    U = torch.rand((B, case.ndim), dtype=torch.float64, device="cuda", generator=gen)
+    m.reset_counters()
+    theta, lnl = m.transform_loglike_device(U)
+    torch.cuda.synchronize()
+    c = m.counters()
+    assert c["n_points"] == B and c["n_solves"] == B * case.n_epochs * case.n_planets
+    assert c["n_cap_hits"] == 0
+    lnl_h = lnl.cpu().numpy()
+    assert np.all(np.isfinite(lnl_h)) and np.all(lnl_h < 0)
+    idx = np.random.default_rng(0).choice(B, 600, replace=False)
+    idx[:3] = [0, B // 2, B - 1]
+    th = theta[torch.from_numpy(idx).cuda()].cpu().numpy()
+    again = m.log_likelihood_batch(th)
+    ok, worst = lnl_close(again, lnl_h[idx])  # another batch size: another summation tree
+    assert ok, worst
+    # and against the plain-C whole-path oracle on a few of those rows
+    from oracle import rv_oracle
+    t, v, s_, ids = case.arrays()
+    want, _, _ = rv_oracle.c_loglike_batch(m.desc_bytes(), t, v, s_, ids.astype(np.int32),
+                                           len(case.insts), th[:40])
+    ok, worst = lnl_close(lnl_h[idx[:40]], want)
+    assert ok, worst
+    m.close()
+
+
 def test_true_anomaly_ffi_vs_reference_binary():
     """rvl_trueanomaly against the outputs of the reference's shipped trueanomaly.so."""
     from evidence_b200 import synth

@@ -18,7 +18,7 @@ th_pin = torch.from_numpy(th_host).pin_memory()
 out_pin = torch.empty(B, dtype=torch.float64).pin_memory()
 ref = None
 
-DEFAULTS = dict(sched=1, phase_items=100, max_split=16, prepare=0, warps=0, slices=0, zero_copy=1,
+DEFAULTS = dict(sched=1, phase_items=200, max_split=8, prepare=0, warps=0, slices=0, zero_copy=1,
                 items_per_warp=4, min_chunks=8)
 
 
