@@ -1070,6 +1070,11 @@ struct rvl_handle {
     size_t cap_gconsts = 0;
     long long cap_ready = 0;
     unsigned seq = 0;
+    // pinned bounce buffers for PAGEABLE caller memory (numpy arrays): a pageable cudaMemcpy is a
+    // synchronous, driver-staged copy (~185 us for 491 KB measured); one CPU memcpy into pinned
+    // memory that the kernels then read / write in place costs ~30 us
+    void *pin_in = nullptr, *pin_out = nullptr, *pin_out2 = nullptr;
+    size_t cap_pin_in = 0, cap_pin_out = 0, cap_pin_out2 = 0;
     unsigned long long *d_trace = nullptr;  // option "trace": per-warp time stamps of the last launch
     int trace_rows = 0;
     double *d_theta = nullptr, *d_u = nullptr, *d_lnl = nullptr, *d_partial = nullptr;
@@ -1442,6 +1447,61 @@ void *pinned_alias(rvl_t *h, const void *p)
     return nullptr;
 }
 
+// Pageable buffers up to this size go through the pinned bounce buffers; larger ones through the
+// driver's own chunked staging (cudaMemcpyAsync), which overlaps its chunks.
+constexpr size_t kBounceMax = (size_t)32 << 20;
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) return true;
+    cudaGetLastError();
+    return false;
+}
+
+int ensure_pin(rvl_t *h, void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return RVL_OK;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr; *cap = 0;
+    const size_t sz = std::max(need, (size_t)1 << 20);
+    CU(h, cudaHostAlloc(buf, sz, cudaHostAllocDefault));
+    *cap = sz;
+    return RVL_OK;
+}
+
+// Input side: returns in *src a PINNED host pointer holding the caller's data (the caller's own
+// buffer if it is pinned, else the bounce buffer after one memcpy), or the caller's pointer
+// unchanged with *pinned = false (too large / bouncing disabled).
+int bounce_in(rvl_t *h, const void *user, size_t nb, const void **src, bool *pinned)
+{
+    *src = user;
+    *pinned = is_pinned(user);
+    if (*pinned || !h->opt_zero_copy || nb == 0 || nb > kBounceMax) return RVL_OK;
+    int rc = ensure_pin(h, &h->pin_in, &h->cap_pin_in, nb);
+    if (rc) return rc;
+    memcpy(h->pin_in, user, nb);
+    *src = h->pin_in;
+    *pinned = true;
+    return RVL_OK;
+}
+
+// Output side: a pinned host pointer the kernels can write in place (the caller's buffer, or a
+// bounce buffer that is copied out after the stream has been synchronised), or NULL.
+int bounce_out(rvl_t *h, void *user, size_t nb, void **buf, size_t *cap, void **dst, bool *copy_back)
+{
+    *copy_back = false;
+    *dst = nullptr;
+    if (!h->opt_zero_copy || !user || nb == 0) return RVL_OK;
+    if (is_pinned(user)) { *dst = user; return RVL_OK; }
+    if (nb > kBounceMax) return RVL_OK;
+    int rc = ensure_pin(h, buf, cap, nb);
+    if (rc) return rc;
+    *dst = *buf;
+    *copy_back = true;
+    return RVL_OK;
+}
+
 int finish_timing(rvl_t *h)
 {
     if (h->timing_pending) {
@@ -1514,6 +1574,9 @@ void rvl_destroy(rvl_t *h)
     cudaFree(h->d_partial); cudaFree(h->d_flags); cudaFree(h->d_counters); cudaFree(h->d_work);
     cudaFree(h->d_consts); cudaFree(h->d_arrive); cudaFree(h->d_trace);
     cudaFree(h->d_gconsts); cudaFree(h->d_ready);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->pin_out2) cudaFreeHost(h->pin_out2);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1722,28 +1785,37 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
     // A pinned theta is read in place (zero-copy): the likelihood kernel reads every row ONCE, with
     // one coalesced warp read (the setup item of a split point, or the point's only item), so the
     // PCIe transfer overlaps the arithmetic instead of preceding it.  When the epoch axis needs
-    // several resident ranges every range would read the row: theta is then staged by a copy, as
-    // pageable theta always is.  A pinned lnL is written in place.
+    // several resident ranges every range would read the row: theta is then staged by a DMA copy.
+    // Pageable buffers (numpy arrays) pass through pinned bounce buffers.  lnL is written in place.
     const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
     Plan pl;
     if (h->cols_dirty) { rc = upload_columns(h); if (rc) return rc; }
     rc = make_plan(h, B, pl);
     if (rc) return rc;
     const bool once = pl.Sm == 1 && (h->opt_setup_items || pl.n_split == 0) && !h->opt_prepare;
-    double *th_dev = (h->opt_zero_copy > 1 || (h->opt_zero_copy == 1 && once))
-                         ? (double *)pinned_alias(h, Theta) : nullptr;
-    double *out_dev = (double *)pinned_alias(h, lnL);
+    const void *src;
+    bool src_pinned;
+    rc = bounce_in(h, Theta, nb, &src, &src_pinned);
+    if (rc) return rc;
+    double *th_dev = (src_pinned && (h->opt_zero_copy > 1 || (h->opt_zero_copy == 1 && once)))
+                         ? (double *)pinned_alias(h, src) : nullptr;
     const bool via_prepare = th_dev != nullptr && !once;
     if (!th_dev) {
         th_dev = h->d_theta;
-        if (nb) CU(h, cudaMemcpyAsync(h->d_theta, Theta, nb, cudaMemcpyHostToDevice, h->stream));
+        if (nb) CU(h, cudaMemcpyAsync(h->d_theta, src, nb, cudaMemcpyHostToDevice, h->stream));
     }
+    void *out_host;
+    bool out_copy;
+    rc = bounce_out(h, lnL, (size_t)B * sizeof(double), &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    if (rc) return rc;
+    double *out_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
     rc = enqueue_loglike(h, nullptr, th_dev, B, out_dev ? out_dev : h->d_lnl, h->stream,
                          h->opt_timing != 0, nullptr, via_prepare);
     if (rc) return rc;
     if (!out_dev)
         CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (out_dev && out_copy) memcpy(lnL, out_host, (size_t)B * sizeof(double));
     return finish_timing(h);
 }
 
@@ -1757,11 +1829,28 @@ int rvl_transform(rvl_t *h, const double *U, int64_t B, double *Theta)
     int rc = ensure_io(h, B);
     if (rc) return rc;
     const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
-    CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
-    rc = enqueue_transform(h, h->d_u, B, h->d_theta, h->stream);
+    // elementwise and HBM-bound on the device, PCIe-bound here: U is read and theta written in
+    // place through pinned memory (the caller's, or the bounce buffers for pageable arrays)
+    const void *src;
+    bool src_pinned;
+    rc = bounce_in(h, U, nb, &src, &src_pinned);
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    const double *u_dev = src_pinned ? (const double *)pinned_alias(h, src) : nullptr;
+    if (!u_dev) {
+        CU(h, cudaMemcpyAsync(h->d_u, src, nb, cudaMemcpyHostToDevice, h->stream));
+        u_dev = h->d_u;
+    }
+    void *out_host;
+    bool out_copy;
+    rc = bounce_out(h, Theta, nb, &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    if (rc) return rc;
+    double *th_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
+    rc = enqueue_transform(h, u_dev, B, th_dev ? th_dev : h->d_theta, h->stream);
+    if (rc) return rc;
+    if (!th_dev)
+        CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (th_dev && out_copy) memcpy(Theta, out_host, nb);
     return RVL_OK;
 }
 
@@ -1777,14 +1866,27 @@ int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, d
     int rc = ensure_io(h, B);
     if (rc) return rc;
     const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
-    // pinned caller buffers are read / written in place by the prepare pass and the kernels
-    const double *u_dev = (const double *)pinned_alias(h, U);
-    double *th_dev = Theta ? (double *)pinned_alias(h, Theta) : nullptr;
-    double *out_dev = (double *)pinned_alias(h, lnL);
+    // pinned buffers (the caller's, or the bounce buffers for pageable arrays) are read / written
+    // in place by the prepare pass and the kernels
+    const void *src;
+    bool src_pinned;
+    rc = bounce_in(h, U, nb, &src, &src_pinned);
+    if (rc) return rc;
+    const double *u_dev = src_pinned ? (const double *)pinned_alias(h, src) : nullptr;
     if (!u_dev) {
-        CU(h, cudaMemcpyAsync(h->d_u, U, nb, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->d_u, src, nb, cudaMemcpyHostToDevice, h->stream));
         u_dev = h->d_u;
     }
+    void *th_host = nullptr, *out_host = nullptr;
+    bool th_copy = false, out_copy = false;
+    if (Theta) {
+        rc = bounce_out(h, Theta, nb, &h->pin_out2, &h->cap_pin_out2, &th_host, &th_copy);
+        if (rc) return rc;
+    }
+    rc = bounce_out(h, lnL, (size_t)B * sizeof(double), &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    if (rc) return rc;
+    double *th_dev = th_host ? (double *)pinned_alias(h, th_host) : nullptr;
+    double *out_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
     rc = enqueue_loglike(h, u_dev, th_dev ? th_dev : h->d_theta, B, out_dev ? out_dev : h->d_lnl,
                          h->stream, h->opt_timing != 0);
     if (rc) return rc;
@@ -1793,6 +1895,8 @@ int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, d
     if (!out_dev)
         CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (th_dev && th_copy) memcpy(Theta, th_host, nb);
+    if (out_dev && out_copy) memcpy(lnL, out_host, (size_t)B * sizeof(double));
     return finish_timing(h);
 }
 

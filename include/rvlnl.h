@@ -158,11 +158,13 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
                    int64_t n_table_doubles);
 /* knobs, by name; unknown name -> RVL_EINVAL:
  *   "timing"    1: record CUDA events around the likelihood kernel (rvl_last_kernel_ms); default 0
- *   "zero_copy" host-buffer calls whose buffers are page-locked (pinned): 1 (default) theta / U are
- *               read and theta / lnL written in place over PCIe by the kernels (each theta row is
- *               read once, coalesced, while other warps compute); theta is staged by one DMA copy
- *               instead when the epoch axis needs several resident ranges; 2: in place even
- *               then (through the once-per-point pass); 0: stage everything
+ *   "zero_copy" host-buffer calls: 1 (default) page-locked (pinned) theta / U are read and theta /
+ *               lnL written in place over PCIe by the kernels (each theta row is read once,
+ *               coalesced, while other warps compute); PAGEABLE buffers up to 32 MiB (numpy arrays)
+ *               are bounced through pinned buffers of the handle with one CPU memcpy instead of the
+ *               driver's synchronous pageable copy; theta is staged by one DMA copy when the epoch
+ *               axis needs several resident ranges; 2: in place even then (through the
+ *               once-per-point pass); 0: stage everything with cudaMemcpyAsync
  *   "variant"   0 optimised kernel (default), 1 conservative cross-check (IEEE division, full sin/cos)
  *   "ilp"       epochs per lane in flight, 1 or 2 (default 2)
  *   "sched"     1 (default): graded work list -- whole points first, then the points at the end of the

@@ -49,3 +49,13 @@ pa, pb = th_np.ctypes.data_as(dp), out_np.ctypes.data_as(dp)
 torch.cuda.synchronize(); t = time.perf_counter()
 for _ in range(1000): m._lib.rvl_loglike(m._h, pa, B, pb)
 print("raw ctypes rvl_loglike           : %.1f us per call" % ((time.perf_counter() - t) / 1000 * 1e6))
+# the sampler's real calling pattern: pageable numpy arrays, transform then likelihood
+m.set_priors(case.priordict)
+U = case.draw_unit(B, seed=3)
+def g(): th = m.prior_transform_batch(U); return m.log_likelihood_batch(th)
+def g2(): return m.transform_loglike_batch(U)
+for zc in (1, 0):
+    m.set_option("zero_copy", zc)
+    print("zero_copy=%d  pageable: loglike %.1f us | transform + loglike %.1f us | fused transform_loglike %.1f us" % (
+        zc, timeit(a2), timeit(g), timeit(g2)))
+m.set_option("zero_copy", 1)
