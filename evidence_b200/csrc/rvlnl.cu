@@ -1070,6 +1070,7 @@ struct rvl_handle {
     size_t cap_gconsts = 0;
     long long cap_ready = 0;
     unsigned seq = 0;
+    unsigned smem_opted = 0;  // kernel builds whose shared-memory opt-in has been set on this device
     // pinned bounce buffers for PAGEABLE caller memory (numpy arrays): a pageable cudaMemcpy is a
     // synchronous, driver-staged copy (~185 us for 491 KB measured); one CPU memcpy into pinned
     // memory that the kernels then read / write in place costs ~30 us
@@ -1334,8 +1335,14 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
 template <int V, int U, int T>
 int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
 {
-    CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               h->smem_optin));
+    // opt in to the large dynamic shared memory once per kernel build and handle (device), not on
+    // every launch: the attribute call is a driver round trip on the host-latency path
+    const unsigned bit = 1u << ((V ? 16 : 0) + (U == 2 ? 8 : 0) + T / 128 - 1);
+    if (!(h->smem_opted & bit)) {
+        CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   h->smem_optin));
+        h->smem_opted |= bit;
+    }
     rv_lnl_kernel<V, U, T><<<pl.grid, std::min(pl.W * 32, T), pl.smem, st>>>(a);
     CU(h, cudaGetLastError());
     return RVL_OK;
