@@ -70,9 +70,11 @@ SYMBOLS = {
     "rvl_set_model": (c_int32, [c_void_p, POINTER(rvl_model_desc)]),
     "rvl_set_priors": (c_int32, [c_void_p, POINTER(rvl_prior_desc), c_int32, _dp, c_int64]),
     "rvl_set_option": (c_int32, [c_void_p, c_char_p, c_int64]),
-    "rvl_transform": (c_int32, [c_void_p, _dp, c_int64, _dp]),
-    "rvl_loglike": (c_int32, [c_void_p, _dp, c_int64, _dp]),
-    "rvl_transform_loglike": (c_int32, [c_void_p, _dp, c_int64, _dp, _dp]),
+    # hot host-buffer calls: plain addresses (c_void_p takes an int or any ctypes pointer), so that
+    # the Python wrappers can pass ndarray.ctypes.data without building pointer objects
+    "rvl_transform": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "rvl_loglike": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "rvl_transform_loglike": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "rvl_transform_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "rvl_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "rvl_loglike_dev_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),

@@ -175,11 +175,17 @@ class RVModel(BaseModel):
 
     def log_likelihood_batch(self, X, out=None):
         """lnL for every row of ``X`` (theta in sorted-parnames order); one kernel launch."""
-        X = self._as_batch(X, "X")
+        if not (type(X) is np.ndarray and X.dtype == np.float64 and X.ndim == 2
+                and X.shape[1] == self.ndim and X.flags.c_contiguous):
+            X = self._as_batch(X, "X")  # (the usual case above skips the conversions)
         B = X.shape[0]
         if out is None:
             out = np.empty(B, dtype=np.float64)
-        self._check(self._lib.rvl_loglike(self._h, _ptr(X), B, _ptr(out)))
+        elif not (out.dtype == np.float64 and out.flags.c_contiguous and out.size >= B):
+            raise ValueError("out must be a C-contiguous float64 array with at least B elements")
+        rc = self._lib.rvl_loglike(self._h, X.ctypes.data, B, out.ctypes.data)
+        if rc != 0:
+            self._check(rc)
         return out
 
     def log_likelihood_device(self, theta, out=None):
