@@ -187,8 +187,11 @@ def _whitening(u):
         return np.diag(np.sqrt(np.maximum(np.diag(cov), 1e-30)))
 
 
-def _slice_moves(rng, loglike, transform, u, lmin, chol, nsteps, max_expand=16, max_shrink=64):
-    """Advance k walkers u[k, d] by nsteps slice moves under L > lmin; all evaluations batched."""
+def _slice_moves(rng, loglike, transform, u, lmin, chol, nsteps, max_expand=16, max_shrink=64,
+                 fused=None):
+    """Advance k walkers u[k, d] by nsteps slice moves under L > lmin; all evaluations batched.
+    ``fused(u) -> (theta, lnL)``, when given, replaces the transform + loglike pair of every
+    evaluation by one call (one device round trip instead of two)."""
     k, d = u.shape
     theta = transform(u)
     lcur = np.full(k, np.nan)
@@ -201,8 +204,11 @@ def _slice_moves(rng, loglike, transform, u, lmin, chol, nsteps, max_expand=16, 
         th = np.zeros_like(points)
         idx = np.where(mask & np.all((points >= 0.0) & (points < 1.0), axis=1))[0]
         if len(idx):
-            th[idx] = transform(points[idx])
-            out[idx] = loglike(th[idx])
+            if fused is not None:
+                th[idx], out[idx] = fused(points[idx])
+            else:
+                th[idx] = transform(points[idx])
+                out[idx] = loglike(th[idx])
             ncall += len(idx)
         return out, th
 
@@ -243,11 +249,13 @@ def _slice_moves(rng, loglike, transform, u, lmin, chol, nsteps, max_expand=16, 
 
 def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, frac_remain=0.01,
                   seed=0, nsteps=None, batch_fraction=0.2, method="slice", max_calls=500_000_000,
-                  verbose=False, **kw):
+                  verbose=False, fused=None, **kw):
     """
     Seeded vectorised nested sampling; see the module docstring.  ``loglike(theta[n, ndim])`` and
     ``transform(u[n, ndim])`` follow UltraNest's ``vectorized=True`` convention.  Returns a
-    ``NestedResult`` (logz, logzerr, ncall, niter, samples, ...).
+    ``NestedResult`` (logz, logzerr, ncall, niter, samples, ...).  ``fused(u[n, ndim]) ->
+    (theta[n, ndim], lnL[n])`` (method='slice'): the device's fused u -> theta -> lnL call; it must
+    return what ``transform`` followed by ``loglike`` returns, and then the run is identical.
     """
     if method == "ellipsoid":
         return nested_sample_ellipsoid(loglike, transform, ndim, nlive=nlive, ndraw=ndraw,
@@ -292,7 +300,7 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
         chol = _whitening(u_live[keep])
         starts = keep[rng.integers(0, len(keep), k)]
         u_new, th_new, l_new, nc = _slice_moves(rng, loglike, transform, u_live[starts].copy(),
-                                                lmin, chol, nsteps)
+                                                lmin, chol, nsteps, fused=fused)
         ncall += nc
         stuck = ~np.isfinite(l_new)  # a walker that never moved is a copy of its start point
         l_new = np.where(stuck, l_live[starts], l_new)

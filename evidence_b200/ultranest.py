@@ -120,7 +120,9 @@ def run(model, rundict, priordict, ultrasettings=None):
     else:
         from .sampler import nested_sample
         os.makedirs(settings["log_dir"], exist_ok=True)
-        res = nested_sample(loglike, prior, ndim, nlive=settings["nlive"],
+        # the device model evaluates u -> theta -> lnL in one call (rvl_transform_loglike)
+        fused = getattr(model, "transform_loglike_batch", None) if hasattr(model, "set_priors") else None
+        res = nested_sample(loglike, prior, ndim, nlive=settings["nlive"], fused=fused,
                             ndraw=settings["ndraw_min"], dlogz=settings["dlogz"],
                             frac_remain=settings["frac_remain"], nsteps=settings["nsteps"],
                             method=settings["builtin_method"],

@@ -25,6 +25,12 @@ def test_lnz_device_vs_cpu_oracle():
     kw = dict(nlive=120, seed=11, nsteps=10)
     dev = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, case.ndim, **kw)
 
+    # the fused u -> theta -> lnL call gives the identical run (same theta bits, same lnL bits)
+    n0 = model.launch_count()
+    fus = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, case.ndim,
+                        fused=model.transform_loglike_batch, **kw)
+    assert fus.logz == dev.logz and fus.ncall == dev.ncall and np.array_equal(fus.samples, dev.samples)
+
     t, v, s, ids = case.arrays()
     desc = model.desc_bytes()
 
@@ -36,7 +42,7 @@ def test_lnz_device_vs_cpu_oracle():
     # the run found the injected planet
     per = np.median(dev.samples[:, case.parnames.index("planet1_period")])
     assert abs(per - case.truth["planet1_period"]) / case.truth["planet1_period"] < 0.02
-    assert model.counters()["n_points"] == dev.ncall
+    assert model.counters()["n_points"] == dev.ncall + fus.ncall
     model.close()
 
 

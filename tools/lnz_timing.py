@@ -1,0 +1,17 @@
+# wall time of one seeded ln Z run (in-repo vectorised sampler) with separate transform + loglike
+# calls vs the fused u -> theta -> lnL call
+import sys, time, numpy as np
+sys.path.insert(0, '.')
+from evidence_b200 import synth
+from evidence_b200.rvmodel import RVModel
+from evidence_b200.sampler import nested_sample
+case = synth.make_case(2, seed=4, n_epochs=300)
+m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
+m.set_priors(case.priordict)
+kw = dict(nlive=400, seed=3, nsteps=20)
+nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, nlive=50, seed=1, nsteps=4)  # warm-up
+for name, fused in (("separate", None), ("fused", m.transform_loglike_batch)):
+    t0 = time.perf_counter()
+    r = nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, fused=fused, **kw)
+    dt = time.perf_counter() - t0
+    print(f"{name:9s}: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e3:.1f} k lnL/s")
