@@ -1,7 +1,7 @@
 // rvfip.cu — FIP-periodogram accumulation on the device (part of librvlnl.so).
 //
 // Reference path replaced (paths relative to the reference checkout):
-//   evidence/fip_criterion.py:303-337   for every posterior sample of every k-planet run: the
+//   evidence/fip_criterion.py:303-338   for every posterior sample of every k-planet run: the
 //       mean motions 2pi/P of its planets (optionally with the 1-day / 30-day aliases), the
 //       frequency-grid bins whose window [nu - w/2, nu + w/2] contains one of them
 //       (two np.searchsorted calls), and  fapnu[run, bins] -= p(k|y) * weight  -- a Python loop
@@ -61,7 +61,7 @@ __global__ void fip_ranges_kernel(const double *nua, const double *nub, int nfre
     int beg[kMaxRanges], end[kMaxRanges];
     int m = 0;
     for (int p = 0; p < k; ++p) {
-        const double f0 = __ddiv_rn(6.283185307179586, periods[i * k + p]);  // 2*np.pi/x (:317)
+        const double f0 = __ddiv_rn(6.283185307179586, periods[i * k + p]);  // 2*np.pi/x (:319)
         const int nv = with_alias ? 5 : 1;
         for (int v = 0; v < nv; ++v) {
             double f = f0;
@@ -69,9 +69,9 @@ __global__ void fip_ranges_kernel(const double *nua, const double *nub, int nfre
             if (v == 2) f = fabs(__dsub_rn(f0, shift_day));    // :323
             if (v == 3) f = fabs(__dadd_rn(f0, shift_month));  // :324
             if (v == 4) f = fabs(__dsub_rn(f0, shift_month));  // :325
-            if (with_alias && !(f <= fmax && f >= fmin)) continue;  // :329-330 (NaN drops out too)
-            const int b = upper_bound(nub, nfreq, f);  // np.searchsorted(nub, f, 'right') (:332)
-            const int e = lower_bound(nua, nfreq, f);  // np.searchsorted(nua, f, 'left')  (:333)
+            if (with_alias && !(f <= fmax && f >= fmin)) continue;  // :330-331 (NaN drops out too)
+            const int b = upper_bound(nub, nfreq, f);  // np.searchsorted(nub, f, 'right') (:333)
+            const int e = lower_bound(nua, nfreq, f);  // np.searchsorted(nua, f, 'left')  (:334)
             if (e <= b) continue;                       // range(b, e) is empty
             // insertion sort by beg
             int j = m++;
@@ -85,7 +85,7 @@ __global__ void fip_ranges_kernel(const double *nua, const double *nub, int nfre
         }
     }
     if (m == 0) return;
-    // fixed-point weight; the scale carries p(k|y) / sum(weights)  (:311, :337)
+    // fixed-point weight; the scale carries p(k|y) / sum(weights)  (:313, :338)
     const long long w = llrint(__dmul_rn(__dmul_rn(weights[i], scale), kFix));
     if (w == 0) return;
     // union of the sorted ranges: every bin of the sample is updated once (fancy-index semantics)

@@ -1,6 +1,6 @@
 // rvorder.cu — posterior planet-ordering on the device (part of librvlnl.so).
 //
-// Reference path replaced: evidence/post_processing.py:104-127 -- a pandas `iterrows` loop that,
+// Reference path replaced: evidence/post_processing.py:104-128 -- a pandas `iterrows` loop that,
 // for every posterior sample whose planet periods are not non-decreasing, rebuilds an index list
 // from np.argsort(periods) and gathers the row through it.  The gather uses the RANK of a column's
 // own planet as the source slot (new[i] = old[planets[rank(p_i)][q_i]]), which is the inverse of

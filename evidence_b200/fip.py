@@ -1,7 +1,7 @@
 """
 FIP periodogram (false inclusion probability) of a set of nested-sampling runs, accumulated on the
 device.  Host-side mirror of the block of the reference's ``fip_criterion.py`` that builds
-``fapnu`` (evidence/fip_criterion.py:230-236, 264-266, 303-337); everything around it in that script
+``fapnu`` (evidence/fip_criterion.py:230-236, 264-266, 303-338); everything around it in that script
 (reading run directories, tables, plots) is not rebuilt.
 
     nu, fapnu = fip_periodogram(runs, logZs, Pmin, Pmax, nfreq, Tobs)
@@ -9,7 +9,7 @@ device.  Host-side mirror of the block of the reference's ``fip_criterion.py`` t
 ``runs[r][k]`` is ``(samples[n, k], weights[n])`` -- the period columns of the posterior samples of
 run ``r`` with ``k`` planets and their weights, as the script collects them (:186-198); entry 0
 (the 0-planet model) is ignored.  The frequency grid and p(k|y) are formed on the host exactly as
-the script does; the per-sample loop (:315-337) runs in ``rvl_fip_accumulate`` (one call per
+the script does; the per-sample loop (:315-338) runs in ``rvl_fip_accumulate`` (one call per
 (run, k) block).  There is no CPU fallback.
 """
 import ctypes
@@ -43,7 +43,7 @@ def posterior_of_k(logZs):
 def accumulate_block(fap_row, nua, nub, samples, weights, pk, Pmin, Pmax, with_alias=False,
                      device=-1):
     """
-    One (run, k) block of the loop nest (:308-337) on the device; ``fap_row`` (float64[nfreq],
+    One (run, k) block of the loop nest (:308-338) on the device; ``fap_row`` (float64[nfreq],
     C-contiguous) is updated in place.  Returns the CUDA-event time of the kernels in ms.
     """
     lib = _abi.load()
@@ -70,7 +70,7 @@ def accumulate_block(fap_row, nua, nub, samples, weights, pk, Pmin, Pmax, with_a
 def fip_periodogram(runs, logZs, Pmin, Pmax, nfreq=50000, Tobs=1.0, coef_window=1.0,
                     with_alias=False, device=-1):
     """
-    ``(nu, fapnu[len(runs), nfreq])`` of evidence/fip_criterion.py:303-337 (``fapnu`` starts at 1
+    ``(nu, fapnu[len(runs), nfreq])`` of evidence/fip_criterion.py:303-338 (``fapnu`` starts at 1
     and loses p(k|y) * weight wherever a sample's planet falls within the window of a frequency).
     ``logZs[k]``: the (median) evidence of the k-planet model (:256), k = 0..nmod-1.
     """
@@ -99,7 +99,7 @@ def planet_tables(parnames, nplanets):
 
 def order_planets(samples, parnames, nplanets, device=-1):
     """
-    The reference's ``order`` option of ``postprocess`` (evidence/post_processing.py:104-127) for a
+    The reference's ``order`` option of ``postprocess`` (evidence/post_processing.py:104-128) for a
     whole posterior at once: rows whose planet periods are not non-decreasing get their planet
     columns permuted exactly as the reference's index list does.  Returns a new array.
     """

@@ -246,7 +246,7 @@ int rvl_plan_describe(const int32_t *in, int64_t B, int64_t *out, int32_t cap);
 int rvl_device_info(rvl_t *h, int32_t *sm_count, int32_t *smem_optin, int32_t *clock_khz);
 
 /* ---- next row of the path: FIP-periodogram accumulation ------------------ */
-/* Replaces the per-sample Python loop of evidence/fip_criterion.py:303-337 for ONE (run, k-planet
+/* Replaces the per-sample Python loop of evidence/fip_criterion.py:303-338 for ONE (run, k-planet
  * model) block: for each of the n posterior samples (periods[n][k], days; weights[n], any positive
  * normalisation) every grid bin j with nua[j] < f < ... -- precisely the bins
  * range(searchsorted(nub, f, 'right'), searchsorted(nua, f, 'left')) of one of the sample's mean
@@ -262,7 +262,7 @@ int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int
                        double *kernel_ms);
 const char *rvl_fip_last_error(void);
 
-/* Replaces the posterior planet-ordering loop of evidence/post_processing.py:104-127: out[n][ndim]
+/* Replaces the posterior planet-ordering loop of evidence/post_processing.py:104-128: out[n][ndim]
  * = samples[n][ndim] with, in every row whose K planet periods (columns period_cols[K]) are not
  * non-decreasing, the columns of the planets (planet_cols[K][Q]: the Q columns of planet p, in
  * parnames order -- :94-102) gathered through the reference's index list,

@@ -8,17 +8,20 @@ tools/fip_bench.py.
 Reference followed (paths relative to the reference checkout):
   evidence/fip_criterion.py:230-236   frequency grid  nu = linspace(2pi/Pmax, 2pi/Pmin, nfreq),
                                       window nu_window = coef * 2pi / Tobs, nua/nub = nu -/+ window/2
-  evidence/fip_criterion.py:303-337   per run, per k-planet model, per posterior sample: mean motions
+  evidence/fip_criterion.py:303-338   per run, per k-planet model, per posterior sample: mean motions
                                       2pi/P of the sample's planets (optionally their 1-day / 30-day
                                       aliases, clipped to the grid's range), the grid bins whose window
                                       contains one of them, and  fapnu[run, bins] -= p(k|y) * weight
   evidence/fip_criterion.py:264-266   p(k|y) = exp(logZ_k - logsumexp(logZ))
 
 Parity status: the reference script executes at import, reads run directories of pickles and needs
-matplotlib, so it cannot be imported here and none of its tests pins this path: PARITY UNPINNED by
-the reference.  `accumulate_literal` transcribes the loop nest statement by statement (same numpy
-calls, same fancy-index update, whose duplicate indices subtract ONCE); `accumulate` is a
-vectorised version of the same arithmetic that tests check against it.
+matplotlib, so it cannot be imported, and none of its tests covers this path.  PINNED instead
+against the reference's OWN STATEMENTS: oracle/make_golden_post.py takes lines 305-338 from the file
+where it lies, executes them on seeded inputs and commits the result (tests/golden/fip_ref.npz);
+`accumulate_literal` -- the same loop nest transcribed statement by statement (same numpy calls,
+same fancy-index update, whose duplicate indices subtract ONCE) -- reproduces it bit for bit, and
+`accumulate`, a vectorised form of the same arithmetic, to 1e-15 (tests/test_fip.py).  The alias
+branch of the reference cannot run (NameError at :321) and stays unpinned.
 """
 import numpy as np
 
@@ -42,7 +45,9 @@ def posterior_of_k(logZs):
 
 
 def sample_frequencies(x, Pmin, Pmax, with_alias):
-    """Mean motions of one sample (fip_criterion.py:316-330)."""
+    """Mean motions of one sample (fip_criterion.py:318-331).  with_alias: the reference's own
+    branch raises NameError (x_freqs is never allocated before :321), so it has no executable
+    behaviour; this is its evident intent -- a fresh [5, k] array per sample."""
     x = np.asarray(x, dtype=np.float64)
     if not with_alias:
         return TWO_PI / x
@@ -59,17 +64,17 @@ def sample_frequencies(x, Pmin, Pmax, with_alias):
 
 
 def accumulate_literal(fap_row, nua, nub, samples, weights, pk, Pmin, Pmax, with_alias=False):
-    """One (run, k) block of fip_criterion.py:308-337, statement by statement.  In place."""
+    """One (run, k) block of fip_criterion.py:308-338, statement by statement.  In place."""
     weights = np.asarray(weights, dtype=np.float64)
-    weights = weights / np.sum(weights)               # :311  normalise weights
-    for i, x in enumerate(samples):                   # :315
+    weights = weights / np.sum(weights)               # :313  normalise weights
+    for i, x in enumerate(samples):                   # :317
         x_freqs = sample_frequencies(x, Pmin, Pmax, with_alias)
-        beg = np.searchsorted(nub, x_freqs, 'right')  # :332
-        end = np.searchsorted(nua, x_freqs, 'left')   # :333
+        beg = np.searchsorted(nub, x_freqs, 'right')  # :333
+        end = np.searchsorted(nua, x_freqs, 'left')   # :334
         listind = []
-        for bi, ei in zip(beg, end):                  # :335-336
+        for bi, ei in zip(beg, end):                  # :336-337
             listind += range(bi, ei)
-        fap_row[listind] -= pk * weights[i]           # :337  (duplicate bins subtract once)
+        fap_row[listind] -= pk * weights[i]           # :338  (duplicate bins subtract once)
     return fap_row
 
 
@@ -111,7 +116,7 @@ def accumulate(fap_row, nua, nub, samples, weights, pk, Pmin, Pmax, with_alias=F
 def fip_periodogram(runs, pky, Pmin, Pmax, nfreq, Tobs, coef_window=1.0, with_alias=False,
                     literal=False):
     """
-    fapnu[run, nfreq] of fip_criterion.py:303-337.  ``runs[r][k]`` = (samples[n, k] periods,
+    fapnu[run, nfreq] of fip_criterion.py:303-338.  ``runs[r][k]`` = (samples[n, k] periods,
     weights[n]) for k = 1..nmod-1 (``runs[r][0]`` is ignored: the 0-planet model has no periods).
     """
     nu, nua, nub = frequency_grid(Pmin, Pmax, nfreq, Tobs, coef_window)

@@ -12,7 +12,9 @@ for three or more planets in cyclic disorder the result is not sorted.  Identica
 identical inputs is the contract, so the device path reproduces exactly this.
 
 Parity status: post_processing.py needs matplotlib/corner at import and no reference test covers
-this loop: PARITY UNPINNED by the reference.
+this loop.  PINNED against the reference's OWN STATEMENTS: oracle/make_golden_post.py executes lines
+93-128 of the file where it lies on seeded posteriors (1-4 planets, a NaN period) and commits input
+and output (tests/golden/order_ref.npz); this transcription reproduces them bit for bit.
 """
 import numpy as np
 
@@ -32,7 +34,7 @@ def planet_tables(parnames, nplanets):
 
 
 def order_samples_literal(samples, parnames, nplanets, kind=None):
-    """post_processing.py:104-127 on a float array samples[n, ndim]; returns a new array.
+    """post_processing.py:104-128 on a float array samples[n, ndim]; returns a new array.
     ``kind``: passed to np.argsort; None is the reference's call.  numpy's default sort is NOT
     stable (its SIMD kernels order exactly equal periods platform-dependently), so rows with tied
     periods have no defined reference answer; the device breaks ties by planet index, which is

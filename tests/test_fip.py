@@ -1,7 +1,9 @@
 """
-FIP-periodogram accumulation: the oracle's vectorised form against its literal
-transcription of evidence/fip_criterion.py:303-337 (CPU), and the device path against the oracle
-(GPU).  Tolerance, stated: 1e-12 absolute on fapnu in [0, 1] -- the reference subtracts sample by
+FIP-periodogram accumulation and posterior planet ordering.  The golden files
+tests/golden/{fip_ref,order_ref}.npz were produced by executing the reference's OWN statements
+(evidence/fip_criterion.py:305-338, evidence/post_processing.py:93-128; oracle/make_golden_post.py).
+CPU: the oracle's literal transcriptions reproduce them bit for bit, its vectorised form to 1e-15.
+GPU: the device paths against the golden files and against the oracle on larger seeded inputs.  Tolerance, stated: 1e-12 absolute on fapnu in [0, 1] -- the reference subtracts sample by
 sample in float64 (rounding ~1e-16 per subtraction, order-dependent); the device accumulates in
 2^-56 fixed point (exact integer sums, one rounding per sample weight).
 """
@@ -11,6 +13,56 @@ import pytest
 from oracle import fip_oracle as fo
 
 TOL = 1e-12
+
+
+def _golden_fip():
+    import json, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "fip_ref.npz"))
+    meta = json.loads(str(z["meta"]))
+    runs = [[None] + [(z[f"samples_r{r}_k{k}"], z[f"weights_r{r}_k{k}"]) for k in range(1, meta["nmod"])]
+            for r in range(meta["n_runs"])]
+    return meta, runs, z["fapnu"]
+
+
+def _golden_order():
+    import json, os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "order_ref.npz"))
+    meta = json.loads(str(z["meta"]))
+    return [(c["K"], c["parnames"], z[f"in_K{c['K']}"], z[f"out_K{c['K']}"]) for c in meta["cases"]]
+
+
+def test_oracle_reproduces_the_reference_statements_fip():
+    """fapnu computed by lines 305-338 of the reference's own file (committed fixture)."""
+    meta, runs, want = _golden_fip()
+    pky = fo.posterior_of_k(meta["logZs"])
+    _, lit = fo.fip_periodogram(runs, pky, meta["Pmin"], meta["Pmax"], meta["nfreq"], meta["Tobs"],
+                                literal=True)
+    assert np.array_equal(lit, want)                       # bit for bit
+    _, vec = fo.fip_periodogram(runs, pky, meta["Pmin"], meta["Pmax"], meta["nfreq"], meta["Tobs"])
+    assert np.max(np.abs(vec - want)) < 5e-15
+    assert want.min() < 0.5 and want.max() == 1.0
+
+
+def test_oracle_reproduces_the_reference_statements_ordering():
+    """Posteriors ordered by lines 93-128 of the reference's own file (committed fixture)."""
+    from oracle.order_oracle import order_samples_literal
+    for K, names, src, want in _golden_order():
+        got = order_samples_literal(src, names, K)
+        assert np.array_equal(got, want, equal_nan=True), K
+        if K >= 2:
+            assert np.any(src != want)                     # the fixture does reorder rows
+
+
+@pytest.mark.gpu
+def test_device_vs_the_reference_statements():
+    from evidence_b200 import fip
+    meta, runs, want = _golden_fip()
+    _, got = fip.fip_periodogram(runs, meta["logZs"], meta["Pmin"], meta["Pmax"], meta["nfreq"],
+                                 meta["Tobs"])
+    assert np.max(np.abs(got - want)) < TOL
+    assert np.array_equal(got == 1.0, want == 1.0)         # the same bins are touched
+    for K, names, src, want_o in _golden_order():
+        assert np.array_equal(fip.order_planets(src, names, K), want_o, equal_nan=True), K
 
 
 def make_runs(seed, n_runs=2, kmax=3, n=400, wild=0.1):
