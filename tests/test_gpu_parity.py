@@ -259,6 +259,34 @@ def test_config5_shape_at_scale_fused_transform():
     m.close()
 
 
+def test_two_handles_from_two_threads(models):
+    """One handle per host thread (the header's threading rule): concurrent calls on separate
+    handles -- separate streams, work counters and scratch -- give the serial results."""
+    import threading
+    meta, z = load_golden("cfg2")
+    theta = np.tile(z["theta"], (8, 1))
+    ms = [device_model(meta, z) for _ in range(2)]
+    want = ms[0].log_likelihood_batch(theta)
+    outs = [[], []]
+
+    def work(i):
+        for r in range(40):
+            b = 100 + 37 * ((r + i) % 9)
+            outs[i].append((b, ms[i].log_likelihood_batch(theta[:b])))
+        outs[i].append((len(theta), ms[i].log_likelihood_batch(theta)))
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(2):
+        assert len(outs[i]) == 41
+        for b, got in outs[i]:
+            ok, worst = lnl_close(got, want[:b])   # another batch size: another summation tree
+            assert ok, (i, b, worst)
+        assert np.array_equal(outs[i][-1][1], want)
+    for m in ms:
+        m.close()
+
+
 def test_true_anomaly_ffi_vs_reference_binary():
     """rvl_trueanomaly against the outputs of the reference's shipped trueanomaly.so."""
     from evidence_b200 import synth
