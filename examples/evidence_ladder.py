@@ -5,7 +5,10 @@ independent run per GPU -- replicas, no collective.
     python examples/evidence_ladder.py --kmax 3                      # one GPU, the k's in sequence
     torchrun --nproc-per-node 6 examples/evidence_ladder.py --kmax 5 # rank r takes k = r, r+6, ...
 
-Each line of output is one JSON record {k, logz, logzerr, ncall, seconds, device}.
+Each line of output is one JSON record {k, logz, logzerr, ncall, seconds, device}.  On one GPU the
+ladder ends with what the reference's fip_criterion.py does with such runs: p(k|y) from the
+evidences and the FIP periodogram of the posterior periods, accumulated on the device
+(evidence_b200.fip), and prints the periods where the false inclusion probability is lowest.
 """
 import argparse
 import json
@@ -17,7 +20,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 
 import numpy as np  # noqa: E402
 
-from evidence_b200 import priors, synth  # noqa: E402
+from evidence_b200 import fip, priors, synth  # noqa: E402
 from evidence_b200.rvmodel import RVModel  # noqa: E402
 from evidence_b200.sampler import nested_sample  # noqa: E402
 
@@ -33,6 +36,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     data = synth.make_case(2, seed=11, n_epochs=args.epochs, n_planets=args.true_planets)
+    runs, logzs = [None] * (args.kmax + 1), [None] * (args.kmax + 1)
     for k in range(rank, args.kmax + 1, world):
         spec = {p: v for p, v in data.prior_spec.items()
                 if not p.startswith("planet") or int(p[6:p.index("_")]) <= k}
@@ -46,10 +50,32 @@ def main():
         model.set_priors(pri)
         t0 = time.perf_counter()
         res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
-                            nlive=args.nlive, seed=100 + k)
+                            nlive=args.nlive, seed=100 + k, fused=model.transform_loglike_batch)
+        cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
+        runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
+        logzs[k] = res.logz
         print(json.dumps({"k": k, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
                           "seconds": time.perf_counter() - t0, "device": dev}), flush=True)
         model.close()
+    if world == 1 and args.kmax >= 1:
+        t, _, _, _ = data.arrays()
+        nu, fapnu = fip.fip_periodogram([runs], logzs, Pmin=1.0, Pmax=1000.0, nfreq=50000,
+                                        Tobs=float(t.max() - t.min()), device=dev)
+        pky = fip.posterior_of_k(logzs)
+        best = np.argsort(fapnu[0])[:2000]
+        peaks = []
+        for j in best:  # lowest FIP first, one entry per well-separated period, FIP < 1/2 only
+            if fapnu[0, j] >= 0.5:
+                break
+            if all(abs(np.log(nu[j] / nu[q])) > 0.05 for q in peaks):
+                peaks.append(j)
+            if len(peaks) == args.true_planets + 1:
+                break
+        print(json.dumps({"p(k|y)": [float(x) for x in pky],
+                          "fip_minima": [{"period": float(2 * np.pi / nu[j]), "fip": float(max(fapnu[0, j], 1e-15))}
+                                         for j in peaks],
+                          "true_periods": [data.truth[f"planet{j}_period"]
+                                           for j in range(1, args.true_planets + 1)]}), flush=True)
 
 
 if __name__ == "__main__":
