@@ -259,6 +259,31 @@ def test_config5_shape_at_scale_fused_transform():
     m.close()
 
 
+def test_iteration_cap_is_counted_not_silent():
+    """The reference aborts a solver call at the cap, leaves nu zero-filled and drops the return
+    code (evidence/rvmodel/__init__.py:490); here a lane that reaches the cap keeps its last
+    iterate and is COUNTED (rvl_counters.n_cap_hits) -- DESIGN.md section 3."""
+    from evidence_b200 import synth
+    from evidence_b200.rvmodel import RVModel
+    case = synth.make_case(2, n_epochs=320)
+    theta = case.draw_theta(500, seed=8)
+    full = RVModel(case.fixedpardict, case.datadict(), case.parnames)
+    want = full.log_likelihood_batch(theta)
+    assert full.counters()["n_cap_hits"] == 0
+    capped = RVModel(case.fixedpardict, case.datadict(), case.parnames, itmax=2)
+    got = capped.log_likelihood_batch(theta)
+    c = capped.counters()
+    assert c["n_cap_hits"] > 0 and c["n_newton_iters"] <= 2 * c["n_solves"]
+    assert np.all(np.isfinite(got))
+    # two Newton steps from E = M are already close for small e: the rows differ, but not wildly
+    assert 0 < np.max(np.abs(got - want)) and np.median(np.abs(got - want) / np.abs(want)) < 0.2
+    # a generous cap changes nothing
+    roomy = RVModel(case.fixedpardict, case.datadict(), case.parnames, itmax=50)
+    assert np.array_equal(roomy.log_likelihood_batch(theta), want)
+    for m in (full, capped, roomy):
+        m.close()
+
+
 def test_two_handles_from_two_threads(models):
     """One handle per host thread (the header's threading rule): concurrent calls on separate
     handles -- separate streams, work counters and scratch -- give the serial results."""
