@@ -15,3 +15,10 @@ for name, fused in (("separate", None), ("fused", m.transform_loglike_batch)):
     r = nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, fused=fused, **kw)
     dt = time.perf_counter() - t0
     print(f"{name:9s}: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e3:.1f} k lnL/s")
+# the same run with a large population: nlive = 4096, half of the live points replaced per round
+# (2048 walkers per device call) -- the regime in which a run is device-bound, not host-bound
+kw = dict(nlive=4096, seed=3, nsteps=20, batch_fraction=0.5)
+t0 = time.perf_counter()
+r = nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, fused=m.transform_loglike_batch, **kw)
+dt = time.perf_counter() - t0
+print(f"population 2048: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e6:.2f} M lnL/s")
