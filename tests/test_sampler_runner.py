@@ -97,3 +97,27 @@ def test_polychord_sorted_priors_are_applied_per_group():
     th = prior(np.array([0.3, 0.25, 0.81]))
     assert th[1] == 0.25 and 1.0 <= th[0] <= th[2] <= 100.0  # sorted within the group
     assert th[2] == pytest.approx(1.0 + 99.0 * 0.9) and th[0] == pytest.approx(1.0 + 99.0 * 0.3 * 0.9)
+
+
+def test_speculative_evaluation_keeps_the_chain():
+    """Evaluating the next m stepping-out positions and shrinkage candidates of every walker in one
+    call is the sequential slice-sampling rule evaluated ahead of time: same chain bit for bit,
+    ~3x fewer (larger) likelihood calls."""
+    calls = {}
+
+    def run(m):
+        n = [0]
+
+        def f(th):
+            n[0] += 1
+            return -0.5 * np.sum((th / 0.7) ** 2, axis=1)
+        r = nested_sample(f, lambda u: -10 + 20 * u, 5, nlive=200, seed=9, nsteps=10, speculate=m)
+        calls[m] = n[0]
+        return r
+    base = run(1)
+    for m in (2, 4, 6):
+        r = run(m)
+        assert r.logz == base.logz and r.niter == base.niter
+        assert np.array_equal(r.samples, base.samples)
+        assert r.ncall >= base.ncall          # the discarded look-ahead evaluations are counted
+    assert calls[4] < 0.45 * calls[1]

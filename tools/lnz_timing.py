@@ -10,11 +10,14 @@ m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
 m.set_priors(case.priordict)
 kw = dict(nlive=400, seed=3, nsteps=20)
 nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, nlive=50, seed=1, nsteps=4)  # warm-up
-for name, fused in (("separate", None), ("fused", m.transform_loglike_batch)):
+for name, fused, spec in (("separate", None, 1), ("fused", m.transform_loglike_batch, 1),
+                          ("fused, look-ahead 4", m.transform_loglike_batch, 4),
+                          ("fused, look-ahead auto", m.transform_loglike_batch, None)):
     t0 = time.perf_counter()
-    r = nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, fused=fused, **kw)
+    r = nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, fused=fused,
+                      speculate=spec, **kw)
     dt = time.perf_counter() - t0
-    print(f"{name:9s}: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e3:.1f} k lnL/s")
+    print(f"{name:24s}: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e3:.1f} k lnL/s")
 # the same run with a large population: nlive = 4096, half of the live points replaced per round
 # (2048 walkers per device call) -- the regime in which a run is device-bound, not host-bound
 kw = dict(nlive=4096, seed=3, nsteps=20, batch_fraction=0.5)
