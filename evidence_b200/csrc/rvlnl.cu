@@ -59,7 +59,8 @@ struct PeerOut {
 // so the items handed out last are the short ones: guided self-scheduling against the tail.
 struct Phase {
     unsigned idx0;
-    int S, cps, pad;
+    int S, cps;
+    int shift;  // log2(S) when S is a power of two (the usual case), else -1
     long long pt0;
     long long part0;  // offset (in doubles) of this phase's partial sums
 };
@@ -650,7 +651,8 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
         while (k + 1 < a.nph && i >= a.ph[k + 1].idx0) ++k;
         const unsigned Sk = (unsigned)a.ph[k].S;
         const unsigned j = i - a.ph[k].idx0;
-        it_jp = j / Sk;
+        const int sh = a.ph[k].shift;
+        it_jp = sh >= 0 ? (j >> sh) : (j / Sk);
         it_ks = (unsigned)k | ((j - it_jp * Sk) << 3);
     };
     if (idx < a.nitems) decode(idx);
@@ -732,9 +734,14 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
                     prod = rvl::mul(prod, __shfl_xor_sync(kFull, prod, o));
                 }
                 esum = __reduce_add_sync(kFull, esum);
-                // sum ln sqrt(var) = 0.5 (ln prod + esum ln 2)
-                const double ld = rvl::fma_((double)esum, rvl::kLn2Hi,
-                                           rvl::fma_((double)esum, rvl::kLn2Lo, log(prod)));
+                // sum ln sqrt(var) = 0.5 (ln prod + esum ln 2); prod < 2^32 is split once more so
+                // that the one logarithm of the item is that of a mantissa (no special cases)
+                double pm;
+                int pe, ph;
+                rvl::split_pos(prod, pm, pe);
+                const double lm = rvl::log_mantissa(pm, ph);
+                const double es = (double)(esum + pe + ph);
+                const double ld = rvl::fma_(es, rvl::kLn2Hi, rvl::fma_(es, rvl::kLn2Lo, lm));
                 S1 = rvl::mul(0.5, ld);
             } else {
                 // a variance that is zero / subnormal / negative / non-finite: plain logs
@@ -1295,7 +1302,10 @@ const char *plan_core(const PlanIn &in, long long B, Plan &pl)
     size_t part = 0;
     for (int i = 0; i < nseg; ++i) {
         Phase &p = pl.ph[pl.nph++];
-        p.idx0 = (unsigned)idx; p.S = seg[i].S; p.cps = cps_of(seg[i].S); p.pad = 0;
+        p.idx0 = (unsigned)idx; p.S = seg[i].S; p.cps = cps_of(seg[i].S);
+        p.shift = -1;
+        for (int b = 0; b < 31; ++b)
+            if ((1 << b) == seg[i].S) p.shift = b;
         p.pt0 = pt; p.part0 = (long long)part;
         const int Stot = Sm * seg[i].S;
         if (Stot > 1) {

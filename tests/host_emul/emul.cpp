@@ -242,7 +242,12 @@ extern "C" int emul_loglike(const rvl_model_desc *mp, const double *t, const dou
                     memcpy(chi, nchi, sizeof chi); memcpy(prod, nprod, sizeof prod);
                 }
                 { int tot = 0; for (int l = 0; l < W; ++l) tot += esum[l]; for (int l = 0; l < W; ++l) esum[l] = tot; }
-                const double ld = fma((double)esum[0], rvl::kLn2Hi, fma((double)esum[0], rvl::kLn2Lo, log(prod[0])));
+                double pm;
+                int32_t pe, ph;
+                rvl::split_pos(prod[0], pm, pe);
+                const double lm = rvl::log_mantissa(pm, ph);
+                const double es = (double)(esum[0] + pe + ph);
+                const double ld = fma(es, rvl::kLn2Hi, fma(es, rvl::kLn2Lo, lm));
                 S1 = 0.5 * ld;
             } else {
                 double acc[W];
