@@ -135,3 +135,51 @@ def test_rejects_bad_input(built_lib):
     out = (ctypes.c_int64 * 64)()
     assert lib.rvl_plan_describe(arr, 10, out, 64) != 0
     assert lib.rvl_plan_describe(None, 10, out, 64) != 0
+
+
+def test_random_plans_cover_exactly_once(built_lib):
+    """Fuzz: 150 random (epochs, batch, kernel build, option) combinations."""
+    rng = np.random.default_rng(2024)
+    for _ in range(150):
+        Ctot = int(rng.choice([1, 2, 3, 7, 8, 31, 32, 33, 64, 157, 313, 400]))
+        B = int(rng.choice([1, 2, 5, 17, 64, 100, 257, 1000]))
+        if Ctot * B > 120_000:
+            B = max(1, 120_000 // Ctot)
+        U = int(rng.choice([1, 2]))
+        kw = dict(W=int(rng.choice([16, 24, 28, 32])), ncol=int(rng.choice([3, 4, 6])),
+                  wstride=int(rng.choice([12, 22, 40, 90])), sm=int(rng.choice([8, 132, 148])),
+                  sched=int(rng.choice([0, 1])), slices=int(rng.choice([0, 0, 0, 2, 3, 9])),
+                  items_per_warp=int(rng.choice([1, 4, 8])), min_chunks=int(rng.choice([1, 4, 8])),
+                  phase_items=int(rng.choice([10, 100, 200, 400])),
+                  max_split=int(rng.choice([1, 2, 8, 16, 64])))
+        plan = describe(Ctot, B, U=U, **kw)
+        Sm, cpm = plan["Sm"], plan["cpm"]
+        assert plan["grid"] % Sm == 0 and cpm % U == 0 and (Sm - 1) * cpm < Ctot <= Sm * cpm, (Ctot, B, U, kw)
+        cover = np.zeros((B, Ctot), dtype=np.int32)
+        fin = np.zeros(B, dtype=np.int32)
+        arrive = np.zeros(max(1, plan["n_split"]), dtype=np.int64)
+        ph = plan["phases"]
+        for sl in range(Sm):
+            c0 = sl * cpm
+            nch = min(cpm, Ctot - c0)
+            for idx in range(plan["nitems"]):
+                k = 0
+                while k + 1 < len(ph) and idx >= ph[k + 1]["idx0"]:
+                    k += 1
+                jp, ss = divmod(idx - ph[k]["idx0"], ph[k]["S"])
+                pt = ph[k]["pt0"] + jp
+                lo = ss * ph[k]["cps"]
+                hi = min(nch, lo + ph[k]["cps"])
+                if hi > lo:
+                    cover[pt, c0 + lo:c0 + hi] += 1
+                Stot = Sm * ph[k]["S"]
+                if Stot == 1:
+                    fin[pt] += 1
+                else:
+                    a = pt - plan["ptS0"]
+                    assert 0 <= a < plan["n_split"]
+                    arrive[a] += 1
+                    if arrive[a] == Stot:
+                        fin[pt] += 1
+                        arrive[a] = 0
+        assert (cover == 1).all() and (fin == 1).all() and (arrive == 0).all(), (Ctot, B, U, kw)
