@@ -14,6 +14,8 @@
  *   evidence/ultranest/__init__.py:125-146    prior(hypercube) / loglike(x) closures
  *   evidence/polychord/__init__.py:130-171    prior(hypercube) / loglike(x) closures
  *   evidence/priors.py:41-42,62-63,82-83,100-101,249-252  closed-form ppf
+ *   evidence/fip_criterion.py:303-338         FIP-periodogram accumulation (next row of the path)
+ *   evidence/post_processing.py:93-128        posterior planet ordering      (next row of the path)
  *
  * Conventions
  *   - plain C types only; caller owns every host buffer; the library owns all
