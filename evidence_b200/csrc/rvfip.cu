@@ -146,6 +146,10 @@ struct Buf {
     void *p = nullptr;
     ~Buf() { if (p) cudaFree(p); }
 };
+struct Ev {  // released on every return path, like Buf
+    cudaEvent_t e = nullptr;
+    ~Ev() { if (e) cudaEventDestroy(e); }
+};
 
 }  // namespace
 
@@ -197,9 +201,10 @@ int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int
     FCU(cudaMemcpy(d_w.p, weights, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     FCU(cudaMemset(d_diff.p, 0, ((size_t)nfreq + 1) * sizeof(unsigned long long)));
 
-    cudaEvent_t e0, e1;
-    FCU(cudaEventCreate(&e0));
-    FCU(cudaEventCreate(&e1));
+    Ev ev0, ev1;
+    FCU(cudaEventCreate(&ev0.e));
+    FCU(cudaEventCreate(&ev1.e));
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     const double two_pi = 6.283185307179586;
     const int tb = 256;
     FCU(cudaEventRecord(e0, 0));
@@ -214,8 +219,6 @@ int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int
     float ms = 0.f;
     FCU(cudaEventElapsedTime(&ms, e0, e1));
     if (kernel_ms) *kernel_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return RVL_OK;
 }
 

@@ -74,6 +74,10 @@ struct Buf {
     void *p = nullptr;
     ~Buf() { if (p) cudaFree(p); }
 };
+struct Ev {  // released on every return path, like Buf
+    cudaEvent_t e = nullptr;
+    ~Ev() { if (e) cudaEventDestroy(e); }
+};
 
 }  // namespace
 
@@ -130,9 +134,10 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
     OCU(cudaMemcpy(d_in.p, samples, nb, cudaMemcpyHostToDevice));
     OCU(cudaMemcpy(d_pl.p, h_planet, RVL_MAX_DIM, cudaMemcpyHostToDevice));
     OCU(cudaMemcpy(d_pos.p, h_pos, RVL_MAX_DIM, cudaMemcpyHostToDevice));
-    cudaEvent_t e0, e1;
-    OCU(cudaEventCreate(&e0));
-    OCU(cudaEventCreate(&e1));
+    Ev ev0, ev1;
+    OCU(cudaEventCreate(&ev0.e));
+    OCU(cudaEventCreate(&ev1.e));
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     const long long total = (long long)n * ndim;
     const int tb = 256;
     OCU(cudaEventRecord(e0, 0));
@@ -145,8 +150,6 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
     float ms = 0.f;
     OCU(cudaEventElapsedTime(&ms, e0, e1));
     if (kernel_ms) *kernel_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return RVL_OK;
 }
 
