@@ -1585,7 +1585,8 @@ void rvl_destroy(rvl_t *h)
 {
     if (!h) return;
     DevGuard g(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    // launches of the *_dev entry points may still be running on caller streams
+    cudaDeviceSynchronize();
     cudaFree(h->d_cols); cudaFree(h->d_inst); cudaFree(h->d_model); cudaFree(h->d_priors);
     cudaFree(h->d_tables); cudaFree(h->d_theta); cudaFree(h->d_u); cudaFree(h->d_lnl);
     cudaFree(h->d_partial); cudaFree(h->d_flags); cudaFree(h->d_counters); cudaFree(h->d_work);
