@@ -117,6 +117,7 @@ class RVModel(BaseModel):
                                       tol=tol, itmax=itmax)
         self._lib = _abi.load()
         self._h = c_void_p()
+        self.device_index = None if device is None else int(device)  # None: the current device
         rc = self._lib.rvl_create(byref(self._h), -1 if device is None else int(device))
         if rc != 0:
             msg = self._lib.rvl_last_error(None).decode()

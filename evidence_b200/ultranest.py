@@ -12,7 +12,7 @@ post-processing and pickles stay compatible.  What changes is the hot loop: the 
 Extra ``ultrasettings`` keys (the "config switch"):
     'vectorized' (True), 'ndraw_min' (4096), 'ndraw_max' (65536), 'seed' (None),
     'stepsampler' ('region-slice' like the reference | 'population-slice' | 'none'),
-    'sampler' ('auto' | 'ultranest' | 'builtin'), 'builtin_method' ('slice' | 'ellipsoid'),
+    'sampler' ('auto' | 'ultranest' | 'builtin'), 'builtin_method' ('slice' | 'slice-device' | 'ellipsoid'),
     'postprocess' (False), 'plot' (False)
 
 UltraNest is a third-party package that is not part of the reference repository.
@@ -37,6 +37,12 @@ except ImportError:
 
 class Output:
     pass
+
+
+def _torch_device(model):
+    import torch
+    idx = getattr(model, "device_index", None)
+    return torch.device("cuda", torch.cuda.current_device() if idx is None else idx)
 
 
 def make_callbacks(model, priordict):
@@ -122,11 +128,22 @@ def run(model, rundict, priordict, ultrasettings=None):
         os.makedirs(settings["log_dir"], exist_ok=True)
         # the device model evaluates u -> theta -> lnL in one call (rvl_transform_loglike)
         fused = getattr(model, "transform_loglike_batch", None) if hasattr(model, "set_priors") else None
-        res = nested_sample(loglike, prior, ndim, nlive=settings["nlive"], fused=fused,
-                            ndraw=settings["ndraw_min"], dlogz=settings["dlogz"],
-                            frac_remain=settings["frac_remain"], nsteps=settings["nsteps"],
-                            method=settings["builtin_method"],
-                            seed=0 if settings["seed"] is None else settings["seed"])
+        if settings["builtin_method"] == "slice-device":
+            # the whole run on the likelihood's device (evidence_b200.sampler_dev)
+            from .sampler_dev import nested_sample_device
+            if not hasattr(model, "transform_loglike_device"):
+                raise ValueError("'builtin_method': 'slice-device' needs the device model")
+            res = nested_sample_device(lambda U: model.transform_loglike_device(U), ndim,
+                                       nlive=settings["nlive"], dlogz=settings["dlogz"],
+                                       frac_remain=settings["frac_remain"], nsteps=settings["nsteps"],
+                                       seed=0 if settings["seed"] is None else settings["seed"],
+                                       device=_torch_device(model))
+        else:
+            res = nested_sample(loglike, prior, ndim, nlive=settings["nlive"], fused=fused,
+                                ndraw=settings["ndraw_min"], dlogz=settings["dlogz"],
+                                frac_remain=settings["frac_remain"], nsteps=settings["nsteps"],
+                                method=settings["builtin_method"],
+                                seed=0 if settings["seed"] is None else settings["seed"])
         logz, logzerr, ncall, samples = res.logz, res.logzerr, res.ncall, res.samples
         name = "b200-nested"
     tf = time.process_time()

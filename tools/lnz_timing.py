@@ -25,3 +25,14 @@ t0 = time.perf_counter()
 r = nested_sample(m.log_likelihood_batch, m.prior_transform_batch, case.ndim, fused=m.transform_loglike_batch, **kw)
 dt = time.perf_counter() - t0
 print(f"population 2048: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e6:.2f} M lnL/s")
+# the whole run on the device (sampler_dev): same model, same settings
+import torch
+from evidence_b200.sampler_dev import nested_sample_device
+fd = lambda U: m.transform_loglike_device(U)
+nested_sample_device(fd, case.ndim, nlive=50, seed=1, nsteps=4)  # warm-up
+for name, kw in (("device-resident", dict(nlive=400, seed=3, nsteps=20)),
+                 ("device-resident, population 2048", dict(nlive=4096, seed=3, nsteps=20, batch_fraction=0.5))):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = nested_sample_device(fd, case.ndim, **kw)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"{name:34s}: ln Z = {r.logz:.3f} +- {r.logzerr:.3f}, {r.ncall} likelihood calls, {dt:.2f} s wall, {r.ncall/dt/1e6:.2f} M lnL/s")
