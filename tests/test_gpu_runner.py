@@ -92,3 +92,18 @@ def test_device_resident_sampler_matches_the_host_sampler():
     assert abs(per - case.truth["planet1_period"]) / case.truth["planet1_period"] < 0.02
     print(f"host-bookkeeping {t_host:.2f} s, device-resident {t_dev:.2f} s")
     model.close()
+
+
+def test_runner_with_the_device_resident_sampler(tmp_path):
+    from evidence_b200 import ultranest as runner
+    from evidence_b200.rvmodel import RVModel
+    case = _case()
+    model = RVModel(case.fixedpardict, case.datadict(pandas=True), case.parnames)
+    rundict = {"target": "synth", "runid": "c1dev", "save_dir": str(tmp_path), "nplanets": 1}
+    out = runner.run(model, rundict, case.priordict,
+                     {"nlive": 60, "sampler": "builtin", "builtin_method": "slice-device",
+                      "seed": 2, "nsteps": 6})
+    assert np.isfinite(out.logZ) and out.logZerr > 0 and out.nlike > 1000
+    assert out.device_counters["n_points"] == out.nlike
+    assert list(out.samples.columns) == model.parnames
+    model.close()
