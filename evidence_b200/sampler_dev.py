@@ -35,15 +35,20 @@ def _whitening(torch, u):
     return torch.where(info.reshape(1, 1) == 0, L, diag)
 
 
-def _slice_moves(torch, gen, fused, u, theta, lmin, chol, nsteps, m, max_expand, max_shrink):
+def _slice_moves(torch, gen, fused, u, theta, lmin, chol, nsteps, m, max_expand, max_shrink,
+                 m_out=None):
     """k walkers, nsteps slice moves each, everything on u.device.  Returns (u, theta, lnL, ncall);
     lnL is NaN for a walker that never moved."""
     k, d = u.shape
     dev, f64 = u.device, u.dtype
     lcur = torch.full((k,), float("nan"), dtype=f64, device=dev)
     rows = torch.arange(k, device=dev)
-    steps = torch.arange(m, device=dev, dtype=f64)
-    isteps = torch.arange(m, device=dev)
+    # stepping out has no sequential dependence at all (the positions are lo - j, hi + j): with
+    # room in the launch every one of the max_expand positions of both sides is evaluated at once
+    # and the phase needs ONE launch and no read-back
+    mo = m if m_out is None else max(1, min(int(m_out), max_expand))
+    steps = torch.arange(mo, device=dev, dtype=f64)
+    isteps = torch.arange(mo, device=dev)
     hi_clamp = 1.0 - 2.0 ** -53
     ncall = 0
 
@@ -68,20 +73,23 @@ def _slice_moves(torch, gen, fused, u, theta, lmin, chol, nsteps, m, max_expand,
         grow_hi = torch.ones(k, dtype=torch.bool, device=dev)
         done_lo = torch.zeros(k, dtype=torch.long, device=dev)
         done_hi = torch.zeros(k, dtype=torch.long, device=dev)
-        for _e in range((max_expand + m - 1) // m):
+        n_out = (max_expand + mo - 1) // mo
+        for _e in range(n_out):
             edges = torch.cat([lo[:, None] - steps[None, :], hi[:, None] + steps[None, :]], dim=1)
             mask = torch.cat([grow_lo[:, None] & (done_lo[:, None] + isteps[None, :] < max_expand),
                               grow_hi[:, None] & (done_hi[:, None] + isteps[None, :] < max_expand)], dim=1)
             ll, _ = evaluate(u[:, None, :] + edges[:, :, None] * dirn[:, None, :])
             above = (ll > lmin) & mask
-            run_lo = torch.cumprod(above[:, :m].to(torch.long), dim=1).sum(dim=1)
-            run_hi = torch.cumprod(above[:, m:].to(torch.long), dim=1).sum(dim=1)
+            run_lo = torch.cumprod(above[:, :mo].to(torch.long), dim=1).sum(dim=1)
+            run_hi = torch.cumprod(above[:, mo:].to(torch.long), dim=1).sum(dim=1)
             lo = lo - run_lo.to(f64)
             hi = hi + run_hi.to(f64)
             done_lo = done_lo + run_lo
             done_hi = done_hi + run_hi
-            grow_lo = grow_lo & (run_lo == m) & (done_lo < max_expand)
-            grow_hi = grow_hi & (run_hi == m) & (done_hi < max_expand)
+            if n_out == 1:
+                break
+            grow_lo = grow_lo & (run_lo == mo) & (done_lo < max_expand)
+            grow_hi = grow_hi & (run_hi == mo) & (done_hi < max_expand)
             if not bool((grow_lo | grow_hi).any()):  # one scalar back per launch
                 break
         # ---- shrinkage: the next m candidates, each drawn as if the ones before it were rejected
@@ -131,6 +139,7 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
     nsteps = nsteps or max(4, 2 * ndim)
     k = max(1, min(int(batch_fraction * nlive), nlive - 2))
     m = max(1, min(6, 512 // k)) if speculate is None else max(1, int(speculate))
+    m_out = max(m, min(max_expand, 4096 // (2 * k)))  # a likelihood launch costs the same up to ~4096 points
     u_live = torch.rand((nlive, ndim), generator=gen, dtype=f64, device=dev)
     th_live, l_live = fused(u_live)
     th_live, l_live = th_live.clone(), l_live.clone()
@@ -159,7 +168,7 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
         starts = keep[torch.randint(0, len(keep), (k,), generator=gen, device=dev)]
         u_new, th_new, l_new, nc = _slice_moves(torch, gen, fused, u_live[starts].clone(),
                                                 th_live[starts].clone(), lmin, chol, nsteps, m,
-                                                max_expand, max_shrink)
+                                                max_expand, max_shrink, m_out=m_out)
         ncall += nc
         stuck = ~torch.isfinite(l_new)  # a walker that never moved is a copy of its start point
         l_new = torch.where(stuck, l_live[starts], l_new)
