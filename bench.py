@@ -5,17 +5,22 @@ bench.py — headline benchmark of the B200-native RV log-likelihood path.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Metric (BASELINE.json): RV lnL evals/sec (K-planet, batched), plus the fraction of the FP64
-roofline.  Workload at every N: BASELINE.json configs[1] -- 2-planet eccentric + linear drift,
-2 instruments, 1000 epochs, one vectorised batch of ndraw = 4096 parameter vectors per step and
-per GPU (weak scaling: rows sharded over ranks, lnL all-gathered over NCCL inside the step).
+Metric (BASELINE.json): RV lnL evals/sec (K-planet, batched) at 1/2/4/8 B200, plus the fraction of
+the FP64 roofline.  Workload at every N: BASELINE.json configs[2], the configuration the metric
+is quoted on -- 4-planet model, 3 instruments, 5000 epochs, a batched lnL sweep; one step = one
+batch of theta per GPU (rows sharded over the ranks, weak scaling; per-rank lnL vectors gathered
+inside the step by the fused all-gather over NVLink).  The batch is a function of --steps only
+(`batch_for`): large enough that K steps are >= 2 s of device work.
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with theta resident in HBM;
-`e2e` = the same metric through the public host-buffer API (pinned host theta -> H2D -> kernel ->
-D2H lnL) ; `roofline` = algorithmic FP64 flops of the likelihood kernel / its CUDA-event time /
-the FP64 peak measured in the same run by a register-resident DFMA loop (MEASURED_PEAKS.json has
-no FP64 row); `cpu_baseline` = the CPU oracle (numpy restatement + the reference's own C Kepler
-solver from oracle/_ref) on the box's host cores.
+`e2e` = the same metric through the public host-buffer call (page-locked host theta -> kernel ->
+gathered lnL in host memory: rvl_loglike at N = 1, rvl_loglike_gather per rank at N > 1);
+`roofline` = algorithmic FP64 flops of the likelihood kernel / its CUDA-event time / the FP64
+peak measured in the same run by a register-resident DFMA loop (MEASURED_PEAKS.json has no FP64
+row); `parity` = max |lnL - reference| over >= 1e4 theta of the bench model evaluated BEFORE the
+timed region (the run exits non-zero when it fails); `gather_check` (N > 1) = the fused
+all-gather's vector against NCCL's; `cpu_baseline` = the reference implementation itself
+(oracle/_ref, staged by oracle/Makefile) on the box's host cores.
 
 `--impl reference` times that CPU implementation alone, on the same config/metric.
 """
@@ -35,8 +40,21 @@ sys.path.insert(0, ROOT)
 
 METRIC = "RV lnL evals/sec (K-planet, batched)"
 UNIT = "lnL/s"
-CONFIG_ID = 2
-BATCH = 4096
+CONFIG_ID = 3          # BASELINE.json configs[2]: N = 5000 epochs, K = 4 planets, 3 instruments
+LATENCY_CONFIG = 2     # configs[1]: the UltraNest ndraw = 4096 call, reported as a latency line
+LATENCY_BATCH = 4096
+STRESS_TOTAL = 10_000_000  # configs[4]: 1e7 theta x 1e4 epochs x 3 planets over all ranks
+NOMINAL_RATE = 4.5e6   # lnL/s/GPU on config 3: only used to size the batch deterministically
+
+
+def batch_for(steps):
+    """theta rows per GPU and step: a power-of-two multiple of 131072 inside configs[2]'s 1e4-1e6
+    range such that `steps` steps are >= 2 s of device work.  A function of --steps only, so that
+    both arms (and every N) state the same config."""
+    b = 131072
+    while steps * b < 2.0 * NOMINAL_RATE and b < 1048576:
+        b *= 2
+    return b
 
 
 def algorithmic_flops(n_epochs, n_planets, drift_order, mean_iters):
@@ -45,10 +63,9 @@ def algorithmic_flops(n_epochs, n_planets, drift_order, mean_iters):
 
 
 def workload_config(case, batch, world):
-    return {"workload": f"config{CONFIG_ID}: {case.n_planets}-planet Keplerian + "
-                        f"{'linear drift' if case.drift else 'no drift'}, {case.n_inst} instruments, "
-                        f"{case.n_epochs} epochs, batch {batch} theta per step per GPU "
-                        f"(UltraNest vectorized ndraw={batch})",
+    return {"workload": f"config{CONFIG_ID} (BASELINE.json configs[2]): {case.n_planets}-planet Keplerian, "
+                        f"{case.n_inst} instruments, {case.n_epochs} epochs, batched lnL sweep, "
+                        f"{batch} theta per step per GPU",
             "n_epochs": case.n_epochs, "n_planets": case.n_planets, "n_inst": case.n_inst,
             "ndim": case.ndim, "batch_per_gpu": batch, "global_batch": batch * world,
             "parallelism": f"rows sharded x{world}, lnL all-gather",
@@ -56,97 +73,191 @@ def workload_config(case, batch, world):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle (test infrastructure) timed on the host cores
+# CPU side: the reference implementation (oracle/_ref: the reference's own RVModel + C solver,
+# staged by oracle/Makefile) or, where that is absent, the restatement (oracle/rv_oracle.py).
+# Test infrastructure: used here as the checker (parity) and as the timed CPU baseline only.
 # ------------------------------------------------------------------------------------------
 _W = {}
 
 
-def _cpu_init(fixed, tables, parnames):
-    from oracle.rv_oracle import OracleRVModel
-    _W["m"] = OracleRVModel(fixed, tables, parnames)
+def _cpu_model(key):
+    """Per worker process: one CPU model per (config, variant) key, built on first use."""
+    if key not in _W:
+        from evidence_b200 import synth
+        from oracle import ref_runner, rv_oracle
+        config, variant = key
+        case = synth.make_case(config)
+        parnames, fixed = variant_names(case, variant)
+        if ref_runner.available():
+            _W[key] = ("reference", ref_runner.make_model(fixed, case.datadict(), parnames))
+        else:
+            _W[key] = ("port", rv_oracle.OracleRVModel(fixed, case.datadict(), parnames))
+    return _W[key]
 
 
-def _cpu_eval(block):
-    return _W["m"].log_likelihood_batch(block)
+def _cpu_eval(task):
+    key, block = task
+    kind, model = _cpu_model(key)
+    if kind == "reference":
+        from oracle import ref_runner
+        return ref_runner.loglike_rows(model, block)
+    return model.log_likelihood_batch(block)
 
 
-def cpu_rate(case, theta, cores, budget_s=12.0):
-    """lnL/s of the CPU oracle on `cores` processes over a bounded sample of `theta`."""
-    import multiprocessing as mp
-    from oracle import rv_oracle
+def cpu_kind():
+    from oracle import ref_runner, rv_oracle
     rv_oracle.build()
-    kind = rv_oracle.solver_kind()
-    tables = case.datadict()
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init,
-                  initargs=(case.fixedpardict, tables, case.parnames)) as pool:
-        probe = theta[: max(cores * 8, 64)]
-        t0 = time.perf_counter()
-        pool.map(_cpu_eval, np.array_split(probe, cores))
-        rate0 = len(probe) / (time.perf_counter() - t0)
-        probe2 = np.tile(theta, (-(-int(rate0) // len(theta)), 1))[: max(len(probe), int(rate0))]
-        t0 = time.perf_counter()  # longer probe: the first one is dominated by start-up costs
-        pool.map(_cpu_eval, np.array_split(probe2, cores * 4))
-        rate0 = len(probe2) / (time.perf_counter() - t0)
-        n = int(max(len(probe), rate0 * budget_s))
-        reps = -(-n // len(theta))
-        sample = np.tile(theta, (reps, 1))[:n]  # the step's rows, repeated to fill the budget
-        t0 = time.perf_counter()
-        pool.map(_cpu_eval, np.array_split(sample, cores * 4))
-        dt = time.perf_counter() - t0
-    return n / dt, n, dt, kind
+    return "reference" if ref_runner.available() else "port"
+
+
+def kind_text(kind):
+    return ("the unmodified reference RVModel.log_likelihood (evidence/rvmodel, staged in oracle/_ref) "
+            "looped over rows, its own trueanomaly.c" if kind == "reference" else
+            "numpy restatement of RVModel.log_likelihood (oracle/rv_oracle.py)")
+
+
+def make_pool(cores):
+    import multiprocessing as mp
+    return mp.get_context("fork").Pool(cores)
+
+
+def pool_rate(pool, cores, key, theta, seconds):
+    """lnL/s of the CPU arm over a bounded sample of `theta` (rows repeated to fill ~`seconds`)."""
+    probe = theta[: max(cores * 2, 32)]
+    t0 = time.perf_counter()  # first touch builds the models in the workers
+    pool.map(_cpu_eval, [(key, b) for b in np.array_split(probe, cores)])
+    t0 = time.perf_counter()
+    pool.map(_cpu_eval, [(key, b) for b in np.array_split(probe, cores)])
+    rate0 = len(probe) / (time.perf_counter() - t0)
+    n = int(max(len(probe), rate0 * seconds))
+    sample = np.tile(theta, (-(-n // len(theta)), 1))[:n]
+    t0 = time.perf_counter()
+    pool.map(_cpu_eval, [(key, b) for b in np.array_split(sample, cores * 4)])
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
 
 
 def run_reference(args, rank, world, emit):
-    """The CPU arm: the oracle on all host cores; every step is a bounded sample of the workload,
-    sized so that warmup + steps together take about two minutes."""
+    """The CPU arm: the reference on all host cores; every step is a bounded sample of the
+    workload, sized so that warmup + steps together take about two minutes."""
     if rank != 0:
         return
-    import multiprocessing as mp
     from evidence_b200 import synth
-    from oracle import rv_oracle
-    rv_oracle.build()
-    kind = rv_oracle.solver_kind()
+    kind = cpu_kind()
     case = synth.make_case(CONFIG_ID)
+    B = batch_for(args.steps)
     cores = os.cpu_count() or 1
-    theta = case.draw_theta(BATCH, seed=1000)
+    theta = case.draw_theta(8192, seed=1000)  # rows of the step's batch (same seed as rank 0's)
     n_steps = args.warmup + args.steps
-    per_step_s = min(12.0, max(0.25, 120.0 / max(1, n_steps)))
-    rates, n = [], 0
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init,
-                  initargs=(case.fixedpardict, case.datadict(), case.parnames)) as pool:
-        probe = theta[: max(cores * 8, 64)]
-        t0 = time.perf_counter()
-        pool.map(_cpu_eval, np.array_split(probe, cores))
-        rate0 = len(probe) / (time.perf_counter() - t0)
-        probe2 = np.tile(theta, (-(-int(rate0 * 2) // len(theta)), 1))[: max(cores * 8, int(rate0 * 2))]
-        t0 = time.perf_counter()  # second, longer probe: the first is dominated by start-up costs
-        pool.map(_cpu_eval, np.array_split(probe2, cores * 4))
-        rate0 = len(probe2) / (time.perf_counter() - t0)
-        n = int(max(cores * 4, rate0 * per_step_s))
+    per_step_s = min(12.0, max(0.5, 110.0 / max(1, n_steps)))
+    key = (CONFIG_ID, "bench")
+    rates = []
+    with make_pool(cores) as pool:
+        rate0, _, _ = pool_rate(pool, cores, key, theta, 2.0)
+        n = int(max(cores * 2, rate0 * per_step_s))
         sample = np.tile(theta, (-(-n // len(theta)), 1))[:n]
-        chunks = np.array_split(sample, cores * 4)
+        tasks = [(key, b) for b in np.array_split(sample, cores * 4)]
         for k in range(n_steps):
             t0 = time.perf_counter()
-            pool.map(_cpu_eval, chunks)
+            pool.map(_cpu_eval, tasks)
             dt = time.perf_counter() - t0
             if k >= args.warmup:
                 rates.append(n / dt)
     value = float(np.mean(rates)) if rates else 0.0
-    sample_txt = (f"{n} lnL evaluations per step (rows of one {BATCH}-theta batch, repeated) on {cores} "
-                  f"processes; numpy restatement of RVModel.log_likelihood; Kepler solver = "
-                  f"{'the reference trueanomaly.c compiled to oracle/_ref' if kind == 'reference' else 'C restatement'}")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * n / value if value else None, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(case, BATCH, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample_txt},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0}}
-    emit(line)
+    sample_txt = (f"{n} lnL evaluations per step (rows of the {B}-theta batch) on {cores} processes; "
+                  + kind_text(kind))
+    emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+          "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": 1e3 * n / value if value else None, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": workload_config(case, B, world),
+          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                           "sample": sample_txt},
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+# ------------------------------------------------------------------------------------------
+# parity sets: theta of the bench model, evaluated on the device before the timed region and on
+# the CPU by the reference (SURVEY.md 8(d) "parity check in the same run")
+# ------------------------------------------------------------------------------------------
+def variant_names(case, variant):
+    """(parnames, fixedpardict) of the bench model ("bench") or of the same model with every planet
+    re-parametrised as secos / sesin / ml0 ("secos": the parametrisation whose e > 1 is the
+    reference's -1e30 sentinel, evidence/rvmodel/__init__.py:425-431, 198-203)."""
+    if variant == "bench":
+        return list(case.parnames), dict(case.fixedpardict)
+    names = []
+    for p in case.parnames:
+        p = p.replace("_ecc", "_secos").replace("_omega", "_sesin").replace("_ma0", "_ml0")
+        names.append(p)
+    return sorted(names), dict(case.fixedpardict)
+
+
+def parity_sets(case):
+    """[(name, variant, theta, abs_bar)]; bar None = reported only."""
+    rng = np.random.default_rng(20260)
+    names = case.parnames
+    K = case.n_planets
+    ecc_cols = [names.index(f"planet{k}_ecc") for k in range(1, K + 1)]
+    sets = []
+    sets.append(("prior_draws", "bench", case.draw_theta(8192, seed=4242), 1e-9))
+    th = case.draw_theta(1024, seed=4243)  # one planet per row just above the prior's e < 0.95
+    for i in range(len(th)):
+        th[i, ecc_cols[i % K]] = rng.uniform(0.95, 0.97)
+    sets.append(("ecc_0.95_0.97", "bench", th, 1e-9))
+    th = case.draw_theta(512, seed=4244)
+    for j, p in enumerate(names):
+        if p.endswith("_jitter"):
+            th[:, j] = 0.0
+    sets.append(("jitter_zero", "bench", th, 1e-9))
+    th = case.draw_theta(512, seed=4245)  # chaotic-Newton regime: bounded by the solver tolerance
+    for i in range(len(th)):
+        th[i, ecc_cols[i % K]] = rng.uniform(0.97, 1.0)
+    sets.append(("ecc_0.97_1.00", "bench", th, 1e-5))
+    # secos / sesin parametrisation: ~30 % of the rows have one planet with e > 1 -> -1e30
+    vnames, _ = variant_names(case, "secos")
+    base = case.draw_theta(512, seed=4246)
+    th = np.empty((512, len(vnames)))
+    for j, p in enumerate(vnames):
+        src = p.replace("_secos", "_ecc").replace("_sesin", "_omega").replace("_ml0", "_ma0")
+        th[:, j] = base[:, names.index(src)]
+    for k in range(1, K + 1):
+        e = rng.uniform(0.0, 0.9, 512)
+        bad = rng.random(512) < 0.3 / K
+        e[bad] = rng.uniform(1.0001, 1.5, bad.sum())
+        w = rng.uniform(0.0, 2 * np.pi, 512)
+        th[:, vnames.index(f"planet{k}_secos")] = np.sqrt(e) * np.cos(w)
+        th[:, vnames.index(f"planet{k}_sesin")] = np.sqrt(e) * np.sin(w)
+    sets.append(("secos_sesin_invalid", "secos", th, 1e-9))
+    return sets
+
+
+def parity_verdict(sets, got, want, kind):
+    """Compare device and CPU values set by set; returns (report, ok)."""
+    out = {"n": 0, "max_abs": 0.0, "sentinels_equal": True, "n_sentinels": 0, "checker": kind,
+           "bar": "abs <= max(1e-9, 1e-13 |lnL|) (SURVEY.md 8d); -1e30 sentinels identical", "sets": {}}
+    ok = True
+    for (name, _, theta, bar), g, w in zip(sets, got, want):
+        sent = w == -1e30
+        sent_ok = bool(np.array_equal(g == -1e30, sent))
+        err = np.where(sent, 0.0, np.abs(g - w))
+        bound = np.maximum(bar, 1e-13 * np.abs(w))
+        passed = bool(sent_ok and np.all(err <= bound))
+        rep = {"n": int(len(w)), "max_abs": float(err.max()), "bar_abs": bar,
+               "max_abs_lnl": float(np.abs(np.where(sent, 0.0, w)).max()),
+               "bit_identical": int(np.sum((g == w) & ~sent)), "sentinels": int(sent.sum()),
+               "pass": passed}
+        out["sets"][name] = rep
+        out["n_sentinels"] += int(sent.sum())
+        out["sentinels_equal"] = out["sentinels_equal"] and sent_ok
+        if bar <= 1e-9:  # the north-star bar; the e > 0.97 set is reported beside it
+            out["n"] += int(len(w))
+            out["max_abs"] = max(out["max_abs"], float(err.max()))
+        else:
+            out["max_abs_high_ecc"] = float(err.max())
+        ok = ok and passed
+    out["pass"] = ok
+    return out, ok
 
 
 # ------------------------------------------------------------------------------------------
@@ -202,50 +313,159 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def sweep(model_factory, case, batch, steps, torch, peak_tflops):
-    """A larger parameter sweep of another BASELINE shape (extra information, N=1 only)."""
-    model = model_factory(case)
-    model.set_option("timing", 1)
-    theta = torch.from_numpy(case.draw_theta(batch, seed=77)).cuda()
-    out = torch.empty(batch, dtype=torch.float64, device="cuda")
-    for _ in range(2):
-        model.log_likelihood_device(theta, out=out)
+# extras (every N): configs[2]'s sweep sizes, the configs[1] latency line, the configs[4] stress
+# ------------------------------------------------------------------------------------------
+class Ranks:
+    """max-over-ranks reduction of device times (every multi-GPU number is the slowest rank's)."""
+
+    def __init__(self, torch, dist, world):
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def max(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def sum(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+
+def timed_ms(torch, fn, reps):
+    """Mean device time of fn() over `reps` calls (CUDA events on the launching stream)."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
     torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def sweep_sizes(model, case, rank, world, ranks, torch, peak):
+    """BASELINE.json configs[2]: the batched lnL sweep at 1e4, 1e5 and 1e6 points in total, rows
+    sharded over the ranks (strong scaling of a fixed total)."""
+    from evidence_b200.multigpu import shard_bounds
+    out = []
+    for total in (10_000, 100_000, 1_000_000):
+        lo, hi, _ = shard_bounds(total, world, rank)
+        theta = torch.from_numpy(case.draw_theta(hi - lo, seed=300 + rank)).cuda()
+        lnl = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+        model.log_likelihood_device(theta, out=lnl)
+        ranks.barrier()
+        model.reset_counters()
+        ms = timed_ms(torch, lambda: model.log_likelihood_device(theta, out=lnl), 3)
+        c = model.counters()
+        mean_it = c["n_newton_iters"] / max(1, c["n_solves"])
+        (ms,) = ranks.max(ms)
+        F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
+        rate = total / (ms * 1e-3)
+        out.append({"total_points": total, "lnl_per_s": rate, "ms": ms,
+                    "frac_of_fp64_peak": rate * F / 1e12 / (peak * world) if peak else None})
+    return out
+
+
+def latency_line(make_model, rank, world, ranks, torch, peak, gather_mode):
+    """BASELINE.json configs[1]: one UltraNest-sized call, ndraw = 4096 theta per GPU (2 planets +
+    linear drift, 1000 epochs).  A latency measurement: the kernel is one launch of ~0.13 ms."""
+    from evidence_b200 import synth
+    case = synth.make_case(LATENCY_CONFIG)
+    model = make_model(case)
+    B = LATENCY_BATCH
+    theta_host = case.draw_theta(B, seed=1000 + rank)
+    theta = torch.from_numpy(theta_host).cuda()
+    lnl = torch.empty(B, dtype=torch.float64, device="cuda")
+    fused = None
+    if world > 1 and gather_mode != "nccl":
+        from evidence_b200.multigpu import FusedGatherLikelihood
+        fused = FusedGatherLikelihood(model, B)
+        step = lambda: fused.evaluate_local(theta)
+    elif world > 1:
+        from evidence_b200.multigpu import ShardedLikelihood
+        sh = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk, out=lnl), case.ndim)
+        step = lambda: sh.evaluate_local(theta)
+    else:
+        step = lambda: model.log_likelihood_device(theta, out=lnl)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    model.set_option("timing", 1)
+    for _ in range(10):
+        step()
+    ranks.barrier()
     model.reset_counters()
-    kms = []
-    for _ in range(steps):
-        model.log_likelihood_device(theta, out=out)
+    steps, tot, kms = 200, 0.0, []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
         kms.append(model.last_kernel_ms())
+    ranks.barrier()
+    tot = float(sum(a.elapsed_time(b) for a, b in ev))
     c = model.counters()
+    model.set_option("timing", 0)
+    # end to end, host buffers, one library call per step
+    th_pin = torch.from_numpy(theta_host).pin_memory()
+    out_pin = torch.empty(B * world, dtype=torch.float64).pin_memory()
+    th_np, out_np = th_pin.numpy(), out_pin.numpy()
+    if fused is not None:
+        call = lambda: fused.evaluate_local_host(th_np, out_np)
+    else:
+        call = lambda: model.log_likelihood_batch(th_np, out=out_np[:B])
+    for _ in range(10):
+        call()
+    ranks.barrier()
+    gc.collect(); gc.disable()
+    marks = [time.perf_counter()]
+    for _ in range(steps):
+        call()
+        marks.append(time.perf_counter())
+    gc.enable()
+    us = np.diff(np.array(marks)) * 1e6
+    e2e_s = marks[-1] - marks[0]
+    tot, e2e_s = ranks.max(tot, e2e_s)
     mean_it = c["n_newton_iters"] / max(1, c["n_solves"])
     F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
-    ms = float(np.mean(kms))
-    rate = batch / (ms * 1e-3)
-    ach = rate * F / 1e12
-    res = {"workload": f"N={case.n_epochs} K={case.n_planets} inst={case.n_inst} batch={batch}",
-           "lnl_per_s": rate, "kepler_solves_per_s": rate * case.n_epochs * case.n_planets,
-           "kernel_ms": ms, "mean_newton_iters": mean_it, "achieved_tflops": ach,
-           "frac_of_fp64_peak": ach / peak_tflops if peak_tflops else None}
+    k_ms = float(np.mean(kms))
+    res = {"workload": f"config{LATENCY_CONFIG} (configs[1]): 2 planets + linear drift, 2 instruments, "
+                       f"1000 epochs, UltraNest vectorized ndraw = {B} theta per GPU and call",
+           "lnl_per_s": world * B * steps / (tot * 1e-3), "us_per_step": 1e3 * tot / steps,
+           "kernel_us": 1e3 * k_ms, "frac_of_fp64_peak": B * F / (k_ms * 1e-3) / 1e12 / peak if peak else None,
+           "e2e_lnl_per_s": world * B * steps / e2e_s,
+           "e2e_us_per_call_percentiles_1_50_99": [float(x) for x in np.percentile(us, [1, 50, 99])]}
     model.close()
     return res
 
 
-def stress(model_factory, torch, peak_tflops, batch=10_000_000):
-    """BASELINE.json configs[4]: raw kernel stress, 1e7 parameter vectors x 1e4 epochs x 3 planets,
-    Kepler solves/s against the FP64 peak.  Everything stays on the device: U ~ torch.rand, the
-    prior transform fused in front of the likelihood (rvl_transform_loglike_dev)."""
+def stress(make_model, rank, world, ranks, torch, peak):
+    """BASELINE.json configs[4]: raw kernel stress, 1e7 parameter vectors x 1e4 epochs x 3 planets
+    (rows sharded over the ranks), Kepler solves/s against the FP64 peak.  Everything stays on the
+    device: U ~ torch.rand, the prior transform fused in front of the likelihood."""
     from evidence_b200 import synth
+    from evidence_b200.multigpu import shard_bounds
     case = synth.make_case(5)
-    model = model_factory(case)
+    model = make_model(case)
     model.set_priors(case.priordict)
     model.set_option("timing", 1)
-    gen = torch.Generator(device="cuda").manual_seed(5)
+    lo, hi, _ = shard_bounds(STRESS_TOTAL, world, rank)
+    rows = hi - lo
+    gen = torch.Generator(device="cuda").manual_seed(5 + rank)
     U = torch.rand((100_000, case.ndim), dtype=torch.float64, device="cuda", generator=gen)
     model.transform_loglike_device(U)  # warm launch
-    torch.cuda.synchronize()
-    U = torch.rand((batch, case.ndim), dtype=torch.float64, device="cuda", generator=gen)
+    U = torch.rand((rows, case.ndim), dtype=torch.float64, device="cuda", generator=gen)
     theta = torch.empty_like(U)
-    lnl = torch.empty(batch, dtype=torch.float64, device="cuda")
+    lnl = torch.empty(rows, dtype=torch.float64, device="cuda")
+    ranks.barrier()
     model.reset_counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -254,17 +474,19 @@ def stress(model_factory, torch, peak_tflops, batch=10_000_000):
     torch.cuda.synchronize()
     total_ms, k_ms = e0.elapsed_time(e1), model.last_kernel_ms()
     c = model.counters()
-    mean_it = c["n_newton_iters"] / max(1, c["n_solves"])
-    F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
-    ach = batch * F / (k_ms * 1e-3) / 1e12
     finite = bool(torch.isfinite(lnl).all().item())
-    res = {"workload": f"configs[4] stress: N={case.n_epochs} K={case.n_planets} batch={batch}, "
-                       "u -> theta -> lnL on the device",
-           "kepler_solves": int(c["n_solves"]), "kernel_ms": k_ms, "total_ms_with_prior_transform": total_ms,
-           "kepler_solves_per_s": c["n_solves"] / (k_ms * 1e-3), "lnl_per_s": batch / (k_ms * 1e-3),
+    total_ms, k_ms = ranks.max(total_ms, k_ms)
+    solves, iters, caps = ranks.sum(c["n_solves"], c["n_newton_iters"], c["n_cap_hits"])
+    mean_it = iters / max(1.0, solves)
+    F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
+    ach = STRESS_TOTAL * F / (k_ms * 1e-3) / 1e12
+    res = {"workload": f"configs[4] stress: N={case.n_epochs} K={case.n_planets}, {STRESS_TOTAL} theta in total "
+                       f"({rows} per GPU), u -> theta -> lnL on the device",
+           "kepler_solves": int(solves), "kernel_ms": k_ms, "total_ms_with_prior_transform": total_ms,
+           "kepler_solves_per_s": solves / (k_ms * 1e-3), "lnl_per_s": STRESS_TOTAL / (k_ms * 1e-3),
            "mean_newton_iters": mean_it, "achieved_tflops": ach,
-           "frac_of_fp64_peak": ach / peak_tflops if peak_tflops else None,
-           "newton_cap_hits": int(c["n_cap_hits"]), "all_finite": finite}
+           "frac_of_fp64_peak": ach / (peak * world) if peak else None,
+           "newton_cap_hits": int(caps), "all_finite": finite}
     model.close()
     return res
 
@@ -272,11 +494,12 @@ def stress(model_factory, torch, peak_tflops, batch=10_000_000):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline and sweeps")
+    ap.add_argument("--batch", type=int, default=0, help="theta per GPU and step (default: batch_for(steps))")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline, sweeps, latency line, stress")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check (profiling runs)")
     ap.add_argument("--gather", default="fused", choices=["fused", "fused-barrier", "nccl"],
                     help="multi-GPU: the all-gather fused into the likelihood launch over NVLink "
                          "symmetric memory (peer stores + completion flags; default), the same with "
@@ -301,9 +524,32 @@ def main():
         run_reference(args, rank, world, emit)
         return
 
+    from evidence_b200 import synth
+    case = synth.make_case(CONFIG_ID)
+    B, K, W = (args.batch or batch_for(args.steps)), args.steps, args.warmup
+
+    # ---- the CPU checker starts first (rank 0): worker processes are forked BEFORE CUDA / NCCL
+    # exist in this process, and evaluate the parity sets while the device warms up
+    pool, psets, want_async, kind = None, None, None, None
+    cores = os.cpu_count() or 1
+    if not args.no_parity:
+        psets = parity_sets(case)
+        if rank == 0:
+            kind = cpu_kind()
+            pool = make_pool(cores)
+            tasks, owner = [], []
+            for si, (_, variant, th, _) in enumerate(psets):
+                for blk in np.array_split(th, max(1, len(th) // 32)):
+                    tasks.append(((CONFIG_ID, variant), blk))
+                    owner.append(si)
+            want_async = pool.map_async(_cpu_eval, tasks, chunksize=1)
+    elif rank == 0 and world == 1 and not args.no_extras:
+        kind = cpu_kind()
+        pool = make_pool(cores)
+
     import torch
     import torch.distributed as dist
-    from evidence_b200 import build, synth
+    from evidence_b200 import build
     from evidence_b200.multigpu import ShardedLikelihood
     from evidence_b200.rvmodel import RVModel
 
@@ -315,36 +561,81 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ranks = Ranks(torch, dist, world)
 
-    def make_model(case):
-        return RVModel(case.fixedpardict, case.datadict(), case.parnames, device=local_rank)
+    def make_model(c, names=None, fixed=None):
+        return RVModel(dict(fixed if fixed is not None else c.fixedpardict), c.datadict(),
+                       list(names if names is not None else c.parnames), device=local_rank)
 
-    case = synth.make_case(CONFIG_ID)
     model = make_model(case)
-    B, K, W = args.batch, args.steps, args.warmup
     theta_host = case.draw_theta(B, seed=1000 + rank)
     theta = torch.from_numpy(theta_host).cuda()
     lnl = torch.empty(B, dtype=torch.float64, device="cuda")
     sharded = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk, out=lnl), case.ndim)
+    fused = None
     gather = "none" if world == 1 else "nccl all_gather"
     if world > 1 and args.gather != "nccl":
         try:  # all-gather fused into the producing kernel over NVLink symmetric memory
             from evidence_b200.multigpu import FusedGatherLikelihood
             sig = "flags" if args.gather == "fused" else "barrier"
-            sharded = FusedGatherLikelihood(model, B, signal=sig)
+            fused = FusedGatherLikelihood(model, B, signal=sig)
             gather = ("fused into the likelihood launch (peer stores over NVLink symmetric memory + "
                       + ("completion flags)" if sig == "flags" else "symmetric-memory barrier)"))
         except Exception as exc:  # symmetric memory unavailable: NCCL all-gather
             print(f"fused gather unavailable ({exc!r}); using NCCL all_gather", file=sys.stderr)
+            fused = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
-        return sharded.evaluate_local(theta)
+        return fused.evaluate_local(theta) if fused is not None else sharded.evaluate_local(theta)
 
-    def barrier():
+    # ---- parity, device side: every rank evaluates the sets on its own GPU (through the C-ABI host
+    # call), rank 0 compares with the CPU reference; the ranks must agree bit for bit
+    parity, parity_ok, got = None, True, None
+    if psets is not None:
+        got = []
+        vmodels = {"bench": model}
+        for name, variant, th, _ in psets:
+            if variant not in vmodels:
+                vn, vf = variant_names(case, variant)
+                vmodels[variant] = make_model(case, vn, vf)
+            got.append(vmodels[variant].log_likelihood_batch(np.ascontiguousarray(th)))
+        for v, m in vmodels.items():
+            if v != "bench":
+                m.close()
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            mine = torch.from_numpy(np.concatenate(got)).cuda()
+            allv = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allv, mine)
+            ranks_agree = bool((allv.view(world, -1) == mine.unsqueeze(0)).all().item())
+        else:
+            ranks_agree = True
+
+    # ---- gather check (N > 1): the fused all-gather's vector against NCCL's, same launch inputs
+    gather_check = None
+    if world > 1:
+        local = model.log_likelihood_device(theta, out=lnl).clone()
+        ref_all = torch.empty(world * B, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(ref_all, local)
+        gather_check = {"n": world * B, "against": "torch.distributed.all_gather_into_tensor (NCCL) of "
+                                                   "rvl_loglike_dev on the same theta"}
+        if fused is not None:
+            g1 = fused.evaluate_local(theta).clone()
+            gather_check["device_call_equal"] = bool(torch.equal(g1, ref_all))
+            if fused.signal == "flags":
+                th_pin0 = torch.from_numpy(theta_host).pin_memory()
+                out0 = torch.empty(world * B, dtype=torch.float64).pin_memory()
+                fused.evaluate_local_host(th_pin0.numpy(), out0.numpy())
+                gather_check["host_call_equal"] = bool(torch.equal(out0, ref_all.cpu()))
+                del th_pin0, out0
+        else:
+            g1 = sharded.evaluate_local(theta)
+            gather_check["device_call_equal"] = bool(torch.equal(g1, ref_all))
+        flags = [float(all(v for k, v in gather_check.items() if k.endswith("_equal")))]
+        t = torch.tensor(flags, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gather_check["pass"] = bool(t.item() == 1.0)
+        del ref_all, g1, local
 
     # At N = 1 a step IS one launch of the likelihood kernel (the work list, the per-point
     # constants and the slice sums all live inside it), so the step's CUDA events time the kernel;
@@ -353,7 +644,7 @@ def main():
     model.set_option("timing", 1 if inner_events else 0)
     for _ in range(W):
         step()
-    barrier()
+    ranks.barrier()
     peak = max(model.fp64_peak_tflops(), model.fp64_peak_tflops())  # after warm-up: clocks are up
     model.reset_counters()
     launches0 = model.launch_count()
@@ -361,7 +652,7 @@ def main():
           for _ in range(K)]
     kms = []
     clocks = ClockSampler(local_rank)
-    barrier()
+    ranks.barrier()
     t_wall = time.perf_counter()
     for k in range(K):
         flush.zero_()  # L2 flush, outside the per-step events
@@ -370,7 +661,7 @@ def main():
         ev[k][1].record()
         if inner_events:
             kms.append(model.last_kernel_ms())
-    barrier()
+    ranks.barrier()
     t_wall = time.perf_counter() - t_wall
     dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     launches = model.launch_count() - launches0
@@ -381,16 +672,19 @@ def main():
     cnt = model.counters()
 
     model.set_option("timing", 0)
-    # ---- end to end: pinned host theta -> H2D -> kernel(s) -> D2H lnL, public host API ----
+    # ---- end to end: ONE public host-buffer call per step -- page-locked host theta read in place
+    # by the kernel over PCIe, lnL (N > 1: the gathered vector of all ranks) back in host memory
     th_pin = torch.from_numpy(theta_host).pin_memory()
-    out_pin = torch.empty(B, dtype=torch.float64).pin_memory()
-    th_np, out_np = th_pin.numpy(), out_pin.numpy()
     out_all_pin = torch.empty(B * world, dtype=torch.float64).pin_memory()
+    th_np, out_np = th_pin.numpy(), out_all_pin.numpy()
+    host_gather = fused is not None and fused.signal == "flags"
 
     def e2e_step():
         if world == 1:
-            model.log_likelihood_batch(th_np, out=out_np)  # rvl_loglike: H2D, kernel, D2H, sync
-        else:  # H2D, kernel, NCCL all-gather, D2H of the gathered vector (what a sampler sees)
+            model.log_likelihood_batch(th_np, out=out_np)  # rvl_loglike
+        elif host_gather:
+            fused.evaluate_local_host(th_np, out_np)       # rvl_loglike_gather
+        else:  # NCCL fallback: H2D, kernel, all-gather, D2H of the gathered vector
             theta.copy_(th_pin, non_blocking=True)
             gathered = sharded.evaluate_local(theta)
             out_all_pin.copy_(gathered, non_blocking=True)
@@ -398,7 +692,7 @@ def main():
 
     for _ in range(W):
         e2e_step()
-    barrier()
+    ranks.barrier()
     # a full collection of the interpreter's heap (torch, numpy, ... imported) takes ~45 ms and
     # would land inside this wall-clock region: collect now, keep the collector off while timing
     gc.collect()
@@ -411,13 +705,11 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     gc.enable()
-    e2e_us = np.diff(np.array(marks)) * 1e6  # per call (every call ends with a stream sync)
+    e2e_ms = np.diff(np.array(marks)) * 1e3  # per call (every call ends with a stream sync)
     clk = clocks.stop()  # the sampler covers both timed regions
+    e2e_equal = bool(np.array_equal(out_np[rank * B:(rank + 1) * B], lnl.cpu().numpy())) if world == 1 or host_gather else None
 
-    if world > 1:
-        red = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(red[0]), float(red[1])
+    dev_ms, e2e_s = ranks.max(dev_ms, e2e_s)
 
     mean_it = cnt["n_newton_iters"] / max(1, cnt["n_solves"])
     F = algorithmic_flops(case.n_epochs, case.n_planets, case.drift, mean_it)
@@ -432,16 +724,23 @@ def main():
         pass
     achieved = B * F / (k_ms * 1e-3) / 1e12
     value = world * B * K / (dev_ms * 1e-3)
+    h2d = int(B * case.ndim * 8)
+    d2h = int(B * world * 8)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(case, B, world), gather=gather),
+        "config": workload_config(case, B, world),
+        "gather": gather,
         "clocks": clk,
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": int(B * case.ndim * 8), "d2h_bytes_per_step": int(B * 8),
-                "us_per_call_percentiles_1_50_99": [float(x) for x in np.percentile(e2e_us, [1, 50, 99])],
-                "us_per_call_max": float(e2e_us.max())},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": ("rvl_loglike (page-locked theta read in place, lnL written in place)" if world == 1 else
+                        "rvl_loglike_gather, one call per rank and step (page-locked theta read in place; gathered "
+                        "lnL of all ranks copied to host memory)" if host_gather else
+                        "torch copies around rvl_loglike_dev + NCCL all_gather"),
+                "ms_per_call_percentiles_1_50_99": [float(x) for x in np.percentile(e2e_ms, [1, 50, 99])],
+                "result_equals_device_path": e2e_equal},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
@@ -451,40 +750,60 @@ def main():
                      "flops_per_lnl": F, "mean_newton_iters": mean_it,
                      "peak_source": "DFMA loop measured in this run (rvl_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 row",
+                     "peak_nominal": 148 * 64 * 2 * 1.965e9 / 1e12,
                      "hbm_bytes_per_lnl": 8 * (case.ndim + 1)},
         "wall_s_timed_region": t_wall,
         "kepler_solves_per_s": value * case.n_epochs * case.n_planets,
         "newton_cap_hits": cnt["n_cap_hits"],
     }
+    if gather_check is not None:
+        line["gather_check"] = gather_check
 
-    if rank == 0 and world == 1 and not args.no_extras:
+    # ---- parity verdict (the CPU side has been running since the start)
+    if psets is not None:
+        if rank == 0:
+            res = want_async.get()
+            want = [np.concatenate([r for r, o in zip(res, owner) if o == si]) for si in range(len(psets))]
+            parity, parity_ok = parity_verdict(psets, got, want, kind)
+            parity["ranks_bit_identical"] = ranks_agree
+            parity["checker_text"] = kind_text(kind)
+            parity_ok = parity_ok and ranks_agree
+            line["parity"] = parity
+
+    if not args.no_extras:
         try:
-            sweeps = []
-            sweeps.append(sweep(make_model, synth.make_case(3), 65536, 5, torch, peak))
-            sweeps.append(sweep(make_model, synth.make_case(5), 32768, 3, torch, peak))
-            line["sweeps"] = sweeps
-            line["stress"] = stress(make_model, torch, peak)
+            line["sweep_total_points"] = sweep_sizes(model, case, rank, world, ranks, torch, peak)
+            line["latency_ndraw4096"] = latency_line(make_model, rank, world, ranks, torch, peak, args.gather)
+            line["stress"] = stress(make_model, rank, world, ranks, torch, peak)
         except Exception as exc:  # extras must never cost the headline line
-            line["sweeps_error"] = repr(exc)
+            line["extras_error"] = repr(exc)
+            if world > 1:
+                raise
+    if rank == 0 and world == 1 and not args.no_extras and pool is not None:
         try:
-            cores = os.cpu_count() or 1
-            rate, n, dt, kind = cpu_rate(case, theta_host, cores, budget_s=12.0)
-            rate1, n1, dt1, _ = cpu_rate(case, theta_host, 1, budget_s=5.0)
+            key = (CONFIG_ID, "bench")
+            rate, n, dt = pool_rate(pool, cores, key, theta_host[:8192], 12.0)
             line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{n} lnL evaluations over the {B} theta rows of one step, {dt:.1f} s on {cores} processes; "
-                          f"numpy restatement of RVModel.log_likelihood with "
-                          f"{'the reference trueanomaly.c (oracle/_ref)' if kind == 'reference' else 'the C restatement of trueanomaly'}"
-                          f"; single core: {rate1:.0f} lnL/s; the step's rows repeated to fill ~12 s",
-                "single_core_value": rate1}
+                "value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": f"{n} lnL evaluations (rows of the step's {B}-theta batch), {dt:.1f} s on {cores} processes; "
+                          + kind_text(kind)}
         except Exception as exc:
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": kind,
                                     "sample": "failed: " + repr(exc)}
+    if pool is not None:
+        pool.terminate()
     if rank == 0:
         emit(line)
     model.close()
+    failed = (not parity_ok) or (gather_check is not None and not gather_check.get("pass", True))
     if world > 1:
+        t = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        failed = bool(t.item() > 0)
         dist.destroy_process_group()
+    if failed:
+        print("bench.py: parity / gather check FAILED (see the JSON line)", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

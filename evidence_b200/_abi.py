@@ -22,7 +22,8 @@ RVL_PHASE_MA0, RVL_PHASE_ML0 = 0, 1
 (RVL_PRIOR_UNIFORM, RVL_PRIOR_JEFFREYS, RVL_PRIOR_MODJEFFREYS, RVL_PRIOR_UNIFORMFREQ,
  RVL_PRIOR_TRUNCRAYLEIGH, RVL_PRIOR_NORMAL, RVL_PRIOR_LOGNORMAL, RVL_PRIOR_TABLE) = range(8)
 
-RVL_ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ESTATE", -5: "ENOMEM"}
+RVL_ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ESTATE", -5: "ENOMEM",
+              -6: "EPEER"}
 
 
 class rvl_param(Structure):
@@ -63,7 +64,10 @@ _dp = POINTER(c_double)
 SYMBOLS = {
     "rvl_abi_version": (c_int32, []),
     "rvl_create": (c_int32, [POINTER(c_void_p), c_int32]),
+    "rvl_create_multi": (c_int32, [POINTER(c_void_p), POINTER(c_int32), c_int32]),
+    "rvl_device_count": (c_int32, [c_void_p, POINTER(c_int32)]),
     "rvl_destroy": (None, [c_void_p]),
+    "rvl_reset": (c_int32, [c_void_p]),
     "rvl_last_error": (c_char_p, [c_void_p]),
     "rvl_set_data": (c_int32, [c_void_p, _dp, _dp, _dp, POINTER(c_int32), c_int32, c_int32]),
     "rvl_set_linpar": (c_int32, [c_void_p, c_int32, _dp, c_int32]),
@@ -81,6 +85,9 @@ SYMBOLS = {
                                           c_int32, c_int64, c_void_p]),
     "rvl_loglike_dev_gather": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),
                                          c_int32, c_int32, c_int64, c_int64, c_uint64, c_void_p]),
+    "rvl_loglike_gather": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),
+                                     c_int32, c_int32, c_int64, c_uint64]),
+    "rvl_gather_status": (c_int32, [c_void_p]),
     "rvl_transform_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                             c_void_p]),
     "rvl_trueanomaly": (c_int32, [c_void_p, _dp, c_int32, c_double, _dp, c_int32, c_double]),
@@ -101,7 +108,10 @@ SYMBOLS = {
     "rvl_plan_describe": (c_int32, [POINTER(c_int32), c_int64, POINTER(c_int64), c_int32]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librvlnl.so")
+# RVL_LIB: another build of the same library (kernel A/B experiments, tools/build_variants.py);
+# it must export the same ABI -- there is still no fallback of any kind
+LIB_PATH = os.environ.get("RVL_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                      "librvlnl.so")
 
 _lib = None
 

@@ -41,17 +41,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    """Compile evidence_b200/csrc/{rvlnl,rvfip,rvorder}.cu -> evidence_b200/librvlnl.so for sm_100a."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile evidence_b200/csrc/{rvlnl,rvfip,rvorder}.cu -> evidence_b200/librvlnl.so for sm_100a.
+    ``defines`` / ``out``: an experimental build beside it (``-DNAME=VALUE`` switches of the kernel
+    source, loaded through the RVL_LIB environment variable by the measurement tools)."""
+    if out is None and not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, SRC_FIP, SRC_ORDER]
+    out = out or OUT
+    cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+           [f"-D{d}" for d in defines] + ["-o", out, SRC, SRC_FIP, SRC_ORDER])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -277,6 +277,20 @@ RVL_HD void advance_medium(double d, double &s, double &c)
     s = add(s, ds);
     c = sub(c, dc);
 }
+// the LAST pass of a solve: every |d| <= tol (1e-4 in the reference): sin d = d - d^3/6 (next term
+// 8e-23), 1 - cos d = d^2/2 (next term d^4/24 = 4e-18, below half an ulp of the values it is
+// subtracted from).  10 instructions.  Valid for |d| < 2e-4.
+RVL_HD void advance_final(double d, double &s, double &c)
+{
+    const double d2 = mul(d, d);
+    const double sd = fma_(mul(d, d2), RVL_K(16), d);
+    const double v = mul(0.5, d2);
+    const double ds = fma_(c, sd, -mul(s, v));
+    const double dc = fma_(s, sd, mul(c, v));
+    s = add(s, ds);
+    c = sub(c, dc);
+}
+constexpr int kHiFinal = 0x3F2A36E2;  // high word of 2e-4: abs_hi(d) < this  =>  |d| < 2e-4
 constexpr double kTinyStep = 0x1p-10;
 constexpr double kSmallStep = 0x1p-5;
 
@@ -284,10 +298,20 @@ constexpr double kSmallStep = 0x1p-5;
 // Given E with (s, c) = (sin E, cos E):  f = (E - ec s) - M  [two grid roundings, as the
 // reference], f' = 1 - ec c, E_new = E - f * rcp(f') [one grid rounding].  Returns E_new - E,
 // which is exact (Sterbenz) and is the quantity the reference thresholds against tol (:21).
+// RVL_FMA_F = 1: E - ec s is formed with ONE rounding (fma) instead of two (product, then
+// difference).  The product's own rounding (<= 1.1e-16 absolute) is below the sin/cos error that
+// is already accepted in s, and four orders below the grid of E the reference rounds on.
+#ifndef RVL_FMA_F
+#define RVL_FMA_F 1
+#endif
 RVL_HD double newton_step(double E, double s, double c, double M, double ec, double &Enew)
 {
     const double r = rcp(fma_(-ec, c, 1.0));
+#if RVL_FMA_F
+    const double f = sub(fma_(-ec, s, E), M);
+#else
     const double f = sub(sub(E, mul(ec, s)), M);
+#endif
     Enew = fma_(-f, r, E);
     return sub(Enew, E);
 }
@@ -302,6 +326,24 @@ RVL_HD double kepler_rv(double s, double c, double ec, double A, double Bs, doub
     const double r = rcp(fma_(-ec, c, 1.0));
     const double num = fma_(Bs, s, mul(A, sub(c, ec)));
     return fma_(num, r, Ce);
+}
+
+// the same with mAec = -(A ec) prepared once per point: A (c - ec) + Bs s = fma(Bs, s, fma(A, c, mAec)),
+// 9 instructions (one rounding fewer; rv only has to be right to a few ulp)
+RVL_HD double kepler_rv2(double s, double c, double ec, double A, double Bs, double Ce, double mAec)
+{
+    const double r = rcp(fma_(-ec, c, 1.0));
+    const double num = fma_(Bs, s, fma_(A, c, mAec));
+    return fma_(num, r, Ce);
+}
+
+// |d| > tol on the bit patterns (positive doubles order like their bits): integer pipe instead of
+// the FP64 pipe.  NaN counts as "not converged" (fabs(nan) > tol is false in the reference, where
+// the loop then ends; here the warp-uniform exit treats NaN as large either way: see solve_planet).
+RVL_HD bool abs_gt(double d, int32_t tol_hi, uint32_t tol_lo)
+{
+    const int32_t h = hi32(d) & 0x7fffffff;
+    return h > tol_hi || (h == tol_hi && (uint32_t)lo32(d) > tol_lo);
 }
 
 // mean anomaly, exactly as the reference forms it (rvmodel/__init__.py:459): three roundings

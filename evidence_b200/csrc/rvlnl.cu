@@ -37,7 +37,16 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kPlanetStride = 8;  // doubles per planet in the per-warp constant block
 constexpr int kModelBytes = (int)((sizeof(rvl_model_desc) + 127) / 128 * 128);
-// per-planet constants: 0 nmot, 1 M0, 2 ec, 3 A, 4 Bs, 5 Ce, 6 epoch
+// per-planet constants: 0 nmot, 1 M0, 2 ec, 3 A, 4 Bs, 5 Ce, 6 epoch, 7 -(A ec)
+#ifndef RVL_INT_TOL
+#define RVL_INT_TOL 1   // |d| > tol on the integer pipe
+#endif
+#ifndef RVL_KRV2
+#define RVL_KRV2 1      // kepler_rv2: A (c - ec) from the prepared -(A ec)
+#endif
+#ifndef RVL_FINAL
+#define RVL_FINAL 1     // shorter series for the last pass of a solve (every |d| <= tol)
+#endif
 
 // Peer buffers of the fused all-gather: device pointers into the other ranks' (and our own)
 // gathered lnL vectors (NVLink peer / symmetric memory).  Passed by value.
@@ -239,6 +248,7 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
     const bool slow = __any_sync(kFull, big || !(ec >= -0.99));
     int trip = 0;  // warp-uniform number of Newton steps taken so far
     const int tol_hi = __double2hiint(tol);
+    const unsigned tol_lo = (unsigned)__double2loint(tol);
 #pragma unroll 2
     for (;;) {
         // warp-wide maximum of the high words of |d|: ONE redux decides the sin/cos path and
@@ -248,7 +258,11 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         for (int u = 0; u < U; ++u) hmax = max(hmax, abs_hi(d[u]));
         const int wmax = (int)__reduce_max_sync(kFull, (unsigned)hmax);
         // (1) bring (sin E, cos E) up to date with the step d just taken
-        if (VARIANT == 0 && wmax < kHiTiny) {
+        if (VARIANT == 0 && RVL_FINAL && wmax < tol_hi && tol_hi < rvl::kHiFinal) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvl::advance_final(d[u], s[u], c[u]);
+            break;  // every |d| < tol: nothing left to iterate (the exit test below, taken early)
+        } else if (VARIANT == 0 && wmax < kHiTiny) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_tiny(d[u], s[u], c[u]);
         } else if (VARIANT == 0 && wmax < kHiSmall) {
@@ -272,7 +286,8 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         // (2) which lanes still iterate (trueanomaly.c:21); the cap (:32-33) bounds the loop
         bool pa[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) pa[u] = fabs(d[u]) > tol;
+        for (int u = 0; u < U; ++u)
+            pa[u] = (VARIANT == 0 && RVL_INT_TOL) ? rvl::abs_gt(d[u], tol_hi, tol_lo) : (fabs(d[u]) > tol);
         if (trip >= itmax || wmax < tol_hi) break;  // high word below tol's: every |d| < tol
         if (wmax == tol_hi) {                       // rare tie on the high word: exact vote
             bool any_left = false;
@@ -301,11 +316,13 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
         }
     }
     const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
+    const double mAec = (VARIANT == 0 && RVL_KRV2) ? lds_f64(pc + 56) : 0.0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         iters[u] += last[u];
         caps += (fabs(d[u]) > tol) ? 1 : 0;
-        rv[u] = rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce);
+        rv[u] = (VARIANT == 0 && RVL_KRV2) ? rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec)
+                                           : rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce);
     }
 }
 
@@ -365,6 +382,7 @@ __device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const doub
         pc[4] = -rvl::mul(rvl::mul(amp, sw), root);
         pc[5] = rvl::mul(amp, rvl::mul(ecc, cw));
         pc[6] = par_of(pl.epoch, row);
+        pc[7] = -rvl::mul(pc[3], ec);
     }
     double *ic = wc + K * kPlanetStride;
     if (lane < m.n_inst) {
@@ -851,16 +869,32 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     }
 }
 
-// consumer side of the fused all-gather: returns once every rank's completion slot holds >= seq
-__global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long seq)
+// consumer side of the fused all-gather: returns once every rank's completion slot holds >= seq.
+// The wait is bounded: after timeout_ns of the device's global timer a lane gives up, records
+// (seq, bit mask of the missing ranks) in `status` (mapped host memory of the handle) and returns, so a
+// peer that died cannot hang this rank's stream forever; the host side reports RVL_EPEER.
+__global__ void wait_flags_kernel(const unsigned long long *flags, int n, unsigned long long seq,
+                                  unsigned long long timeout_ns, unsigned long long *status)
 {
     if ((int)threadIdx.x < n) {
-        unsigned long long v;
+        unsigned long long v, t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x)
                          : "memory");
             if (v >= seq) break;
             __nanosleep(64);
+            if ((++spins & 1023u) == 0u) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > timeout_ns) {
+                    if (status) {
+                        atomicMax(status, seq);                                // which exchange
+                        atomicOr(status + 1, 1ull << threadIdx.x);             // who is missing
+                    }
+                    break;
+                }
+            }
         }
     }
 }
@@ -1108,6 +1142,16 @@ struct rvl_handle {
     uint64_t n_points = 0, n_solves = 0, launches = 0;
     double last_ms = 0.0;
     bool timing_pending = false;
+
+    // fused all-gather: bounded wait.  status[0] = seq of the exchange that timed out (0 = none),
+    // status[1] = bit mask of the ranks that never signalled; mapped host memory, written by
+    // wait_flags_kernel, read by the host after the stream has been synchronised
+    unsigned long long *h_status = nullptr, *d_status = nullptr;
+    long long opt_gather_timeout_ms = 10000;
+
+    // rvl_create_multi: this handle only fans out to one child handle per device (rows of every
+    // host-buffer call are split into contiguous blocks, one per child)
+    std::vector<rvl_handle *> kids;
 };
 
 namespace {
@@ -1332,8 +1376,10 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     in.ncol = h->ncol;
     in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1) & ~1;
     in.wblock = in.wstride + ((m.ndim + 1) & ~1);
-    in.U = (h->opt_variant == 0 && h->opt_ilp == 2) ? 2 : 1;
-    in.W = std::max(1, std::min(32, h->opt_warps > 0 ? h->opt_warps : (in.U == 2 ? 28 : 32)));
+    in.U = h->opt_variant == 0 ? h->opt_ilp : 1;
+    const int w_default = in.U == 1 ? 32 : in.U == 2 ? 28 : in.U == 3 ? 20 : 16;
+    const int w_max = in.U <= 2 ? 32 : in.U == 3 ? 20 : 16;
+    in.W = std::max(1, std::min(w_max, h->opt_warps > 0 ? h->opt_warps : w_default));
     in.sm_count = h->sm_count; in.smem_optin = h->smem_optin;
     in.sched = h->opt_sched; in.slices = h->opt_slices; in.items_per_warp = h->opt_items_per_warp;
     in.min_chunks = h->opt_min_chunks; in.phase_items = h->opt_phase_items;
@@ -1347,7 +1393,7 @@ int launch_lnl_v(rvl_t *h, const KArgs &a, const Plan &pl, cudaStream_t st)
 {
     // opt in to the large dynamic shared memory once per kernel build and handle (device), not on
     // every launch: the attribute call is a driver round trip on the host-latency path
-    const unsigned bit = 1u << ((V ? 16 : 0) + (U == 2 ? 8 : 0) + T / 128 - 1);
+    const unsigned bit = V ? (1u << 31) : (1u << ((U - 1) * 8 + T / 128 - 1));
     if (!(h->smem_opted & bit)) {
         CU(h, cudaFuncSetAttribute(rv_lnl_kernel<V, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    h->smem_optin));
@@ -1430,6 +1476,8 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     else if (pl.U == 2 && pl.W <= 24) rc = launch_lnl_v<0, 2, 768>(h, a, pl, st);
     else if (pl.U == 2 && pl.W <= 28) rc = launch_lnl_v<0, 2, 896>(h, a, pl, st);
     else if (pl.U == 2) rc = launch_lnl_v<0, 2, 1024>(h, a, pl, st);
+    else if (pl.U == 3) rc = launch_lnl_v<0, 3, 640>(h, a, pl, st);
+    else if (pl.U == 4) rc = launch_lnl_v<0, 4, 512>(h, a, pl, st);
     else rc = launch_lnl_v<0, 1, 1024>(h, a, pl, st);
     if (rc) return rc;
     if (timed) { CU(h, cudaEventRecord(h->ev1, st)); h->timing_pending = true; }
@@ -1530,6 +1578,195 @@ int finish_timing(rvl_t *h)
     return RVL_OK;
 }
 
+// ---- host-buffer calls in two halves: enqueue everything on the handle's stream, then wait and
+// copy the bounce buffers back.  A multi-device handle runs the first half on every child before
+// the second half of any, so the devices work concurrently under ONE host thread.
+struct HostCall {
+    double *lnL = nullptr, *Theta = nullptr;  // caller buffers that still need a copy-back
+    void *lnl_host = nullptr, *th_host = nullptr;
+    size_t lnl_bytes = 0, th_bytes = 0;
+};
+
+int hostcall_end(rvl_t *h, HostCall &hc)
+{
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (hc.Theta) memcpy(hc.Theta, hc.th_host, hc.th_bytes);
+    if (hc.lnL) memcpy(hc.lnL, hc.lnl_host, hc.lnl_bytes);
+    return finish_timing(h);
+}
+
+// theta (host) -> lnL (host), everything enqueued on h->stream; no synchronisation.
+// A pinned theta is read in place (zero-copy): the likelihood kernel reads every row ONCE, with
+// one coalesced warp read (the setup item of a split point, or the point's only item), so the
+// PCIe transfer overlaps the arithmetic instead of preceding it.  When the epoch axis needs
+// several resident ranges every range would read the row: theta is then staged by a DMA copy.
+// Pageable buffers (numpy arrays) pass through pinned bounce buffers.  lnL is written in place.
+int loglike_begin(rvl_t *h, const double *Theta, long long B, double *lnL, HostCall &hc,
+                  const PeerOut *peers = nullptr, double *dev_out = nullptr)
+{
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
+    Plan pl;
+    if (h->cols_dirty) { rc = upload_columns(h); if (rc) return rc; }
+    rc = make_plan(h, B, pl);
+    if (rc) return rc;
+    const bool once = pl.Sm == 1 && (h->opt_setup_items || pl.n_split == 0) && !h->opt_prepare;
+    const void *src;
+    bool src_pinned;
+    rc = bounce_in(h, Theta, nb, &src, &src_pinned);
+    if (rc) return rc;
+    double *th_dev = (src_pinned && (h->opt_zero_copy > 1 || (h->opt_zero_copy == 1 && once)))
+                         ? (double *)pinned_alias(h, src) : nullptr;
+    const bool via_prepare = th_dev != nullptr && !once;
+    if (!th_dev) {
+        th_dev = h->d_theta;
+        if (nb) CU(h, cudaMemcpyAsync(h->d_theta, src, nb, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (dev_out)  // the caller collects the result from device memory itself (gather variant)
+        return enqueue_loglike(h, nullptr, th_dev, B, dev_out, h->stream, h->opt_timing != 0, peers,
+                               via_prepare);
+    void *out_host;
+    bool out_copy;
+    rc = bounce_out(h, lnL, (size_t)B * sizeof(double), &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    if (rc) return rc;
+    double *out_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
+    rc = enqueue_loglike(h, nullptr, th_dev, B, out_dev ? out_dev : h->d_lnl, h->stream,
+                         h->opt_timing != 0, peers, via_prepare);
+    if (rc) return rc;
+    if (!out_dev)
+        CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (out_dev && out_copy) { hc.lnL = lnL; hc.lnl_host = out_host; hc.lnl_bytes = (size_t)B * sizeof(double); }
+    return RVL_OK;
+}
+
+int transform_begin(rvl_t *h, const double *U, long long B, double *Theta, HostCall &hc)
+{
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
+    // elementwise and HBM-bound on the device, PCIe-bound here: U is read and theta written in
+    // place through pinned memory (the caller's, or the bounce buffers for pageable arrays)
+    const void *src;
+    bool src_pinned;
+    rc = bounce_in(h, U, nb, &src, &src_pinned);
+    if (rc) return rc;
+    const double *u_dev = src_pinned ? (const double *)pinned_alias(h, src) : nullptr;
+    if (!u_dev) {
+        CU(h, cudaMemcpyAsync(h->d_u, src, nb, cudaMemcpyHostToDevice, h->stream));
+        u_dev = h->d_u;
+    }
+    void *out_host;
+    bool out_copy;
+    rc = bounce_out(h, Theta, nb, &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    if (rc) return rc;
+    double *th_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
+    rc = enqueue_transform(h, u_dev, B, th_dev ? th_dev : h->d_theta, h->stream);
+    if (rc) return rc;
+    if (!th_dev)
+        CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (th_dev && out_copy) { hc.Theta = Theta; hc.th_host = out_host; hc.th_bytes = nb; }
+    return RVL_OK;
+}
+
+int transform_loglike_begin(rvl_t *h, const double *U, long long B, double *Theta, double *lnL,
+                            HostCall &hc)
+{
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
+    // pinned buffers (the caller's, or the bounce buffers for pageable arrays) are read / written
+    // in place by the prepare pass and the kernels
+    const void *src;
+    bool src_pinned;
+    rc = bounce_in(h, U, nb, &src, &src_pinned);
+    if (rc) return rc;
+    const double *u_dev = src_pinned ? (const double *)pinned_alias(h, src) : nullptr;
+    if (!u_dev) {
+        CU(h, cudaMemcpyAsync(h->d_u, src, nb, cudaMemcpyHostToDevice, h->stream));
+        u_dev = h->d_u;
+    }
+    void *th_host = nullptr, *out_host = nullptr;
+    bool th_copy = false, out_copy = false;
+    if (Theta) {
+        rc = bounce_out(h, Theta, nb, &h->pin_out2, &h->cap_pin_out2, &th_host, &th_copy);
+        if (rc) return rc;
+    }
+    rc = bounce_out(h, lnL, (size_t)B * sizeof(double), &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    if (rc) return rc;
+    double *th_dev = th_host ? (double *)pinned_alias(h, th_host) : nullptr;
+    double *out_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
+    rc = enqueue_loglike(h, u_dev, th_dev ? th_dev : h->d_theta, B, out_dev ? out_dev : h->d_lnl,
+                         h->stream, h->opt_timing != 0);
+    if (rc) return rc;
+    if (Theta && !th_dev)
+        CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (!out_dev)
+        CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (th_dev && th_copy) { hc.Theta = Theta; hc.th_host = th_host; hc.th_bytes = nb; }
+    if (out_dev && out_copy) { hc.lnL = lnL; hc.lnl_host = out_host; hc.lnl_bytes = (size_t)B * sizeof(double); }
+    return RVL_OK;
+}
+
+// ---- multi-device handle (rvl_create_multi): contiguous row blocks, one per child ----------------
+// mode 0: Theta -> lnL; 1: U -> Theta; 2: U -> (Theta), lnL.  Child i owns rows
+// [i*ceil(B/n), min(B, (i+1)*ceil(B/n))): the partition of SURVEY.md 8(e).  Every child reads its
+// block of the caller's (pinned) buffer in place and writes its block of the result in place, so
+// the "gather" of the single-process path is the kernels' own stores.
+int multi_fail(rvl_t *h, rvl_t *kid, int rc)
+{
+    h->err = "device " + std::to_string(kid->device) + ": " + kid->err;
+    return rc;
+}
+
+int multi_rows(rvl_t *h, const double *in, const double *U, double *Theta, double *lnL, long long B,
+               int mode)
+{
+    if (B == 0) return RVL_OK;
+    const int n = (int)h->kids.size();
+    const long long per = (B + n - 1) / n;
+    std::vector<HostCall> hc((size_t)n);
+    std::vector<char> live((size_t)n, 0);
+    int rc = RVL_OK;
+    for (int i = 0; i < n && rc == RVL_OK; ++i) {
+        const long long lo = std::min(B, (long long)i * per), hi = std::min(B, lo + per);
+        if (hi <= lo) continue;
+        rvl_t *k = h->kids[i];
+        if (mode != 1 && (!k->have_data || !k->have_model)) return fail(h, RVL_ESTATE, "set data and model first");
+        if (mode != 0 && !k->have_priors) return fail(h, RVL_ESTATE, "set priors first");
+        if (mode == 2 && k->prior_ndim != k->model.ndim) return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
+        const size_t nd = (size_t)(mode == 0 ? k->model.ndim : k->prior_ndim);
+        DevGuard g(k->device);
+        if (mode == 0) rc = loglike_begin(k, in + (size_t)lo * nd, hi - lo, lnL + lo, hc[i]);
+        else if (mode == 1) rc = transform_begin(k, U + (size_t)lo * nd, hi - lo, Theta + (size_t)lo * nd, hc[i]);
+        else rc = transform_loglike_begin(k, U + (size_t)lo * nd, hi - lo,
+                                          Theta ? Theta + (size_t)lo * nd : nullptr, lnL + lo, hc[i]);
+        if (rc) rc = multi_fail(h, k, rc); else live[i] = 1;
+    }
+    for (int i = 0; i < n; ++i) {  // always drain what was enqueued, even after a failure
+        if (!live[i]) continue;
+        rvl_t *k = h->kids[i];
+        DevGuard g(k->device);
+        const int r2 = hostcall_end(k, hc[i]);
+        if (r2 && rc == RVL_OK) rc = multi_fail(h, k, r2);
+    }
+    return rc;
+}
+
+// status of the bounded wait of the fused all-gather (after the stream has been synchronised)
+int check_gather_status(rvl_t *h)
+{
+    if (h->h_status && h->h_status[0] != 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf,
+                 "fused all-gather timed out after %lld ms: exchange %llu, ranks missing (bit mask) 0x%llx",
+                 h->opt_gather_timeout_ms, h->h_status[0], h->h_status[1]);
+        h->h_status[0] = 0; h->h_status[1] = 0;
+        return fail(h, RVL_EPEER, buf);
+    }
+    return RVL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1577,13 +1814,65 @@ int rvl_create(rvl_t **out, int device)
     if ((ce = cudaMalloc(&h->d_work, sizeof(unsigned) * (size_t)(h->sm_count + 1))) != cudaSuccess) return bail("malloc", ce);
     if ((ce = cudaMemset(h->d_work, 0, sizeof(unsigned) * (size_t)(h->sm_count + 1))) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMalloc(&h->d_model, sizeof(rvl_model_desc))) != cudaSuccess) return bail("malloc", ce);
+    if ((ce = cudaHostAlloc((void **)&h->h_status, 2 * sizeof(unsigned long long), cudaHostAllocMapped)) != cudaSuccess) return bail("status word", ce);
+    h->h_status[0] = 0; h->h_status[1] = 0;
+    if ((ce = cudaHostGetDevicePointer((void **)&h->d_status, h->h_status, 0)) != cudaSuccess) return bail("status word", ce);
     *out = h;
+    return RVL_OK;
+}
+
+int rvl_create_multi(rvl_t **out, const int32_t *devices, int32_t n_devices)
+{
+    if (!out) return fail(nullptr, RVL_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RVL_ENODEV,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                        " (librvlnl has no CPU fallback)");
+    if (n_devices < 0 || n_devices > RVL_MAX_PEERS || (n_devices > 0 && !devices))
+        return fail(nullptr, RVL_EINVAL, "bad device list");
+    std::vector<int> devs;
+    if (n_devices == 0) for (int d = 0; d < std::min(ndev, RVL_MAX_PEERS); ++d) devs.push_back(d);  // every device of the box
+    else devs.assign(devices, devices + n_devices);
+    for (size_t i = 0; i < devs.size(); ++i)
+        for (size_t j = 0; j < i; ++j)
+            if (devs[i] == devs[j]) return fail(nullptr, RVL_EINVAL, "device listed twice");
+    rvl_t *h = new (std::nothrow) rvl_handle();
+    if (!h) return fail(nullptr, RVL_ENOMEM, "out of host memory");
+    h->device = devs[0];
+    for (int d : devs) {
+        rvl_t *k = nullptr;
+        const int rc = rvl_create(&k, d);
+        if (rc) {  // g_create_error holds the reason
+            const std::string msg = "device " + std::to_string(d) + ": " + g_create_error;
+            rvl_destroy(h);
+            return fail(nullptr, rc, msg);
+        }
+        h->kids.push_back(k);
+    }
+    h->sm_count = h->kids[0]->sm_count; h->smem_optin = h->kids[0]->smem_optin; h->clock_khz = h->kids[0]->clock_khz;
+    *out = h;
+    return RVL_OK;
+}
+
+int rvl_device_count(rvl_t *h, int32_t *n)
+{
+    if (!h || !n) return RVL_EINVAL;
+    *n = h->kids.empty() ? 1 : (int32_t)h->kids.size();
     return RVL_OK;
 }
 
 void rvl_destroy(rvl_t *h)
 {
     if (!h) return;
+    if (!h->kids.empty()) {
+        for (rvl_t *k : h->kids) rvl_destroy(k);
+        h->kids.clear();
+        delete h;
+        return;
+    }
     DevGuard g(h->device);
     // launches of the *_dev entry points may still be running on caller streams
     cudaDeviceSynchronize();
@@ -1595,6 +1884,7 @@ void rvl_destroy(rvl_t *h)
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     if (h->pin_out2) cudaFreeHost(h->pin_out2);
+    if (h->h_status) cudaFreeHost(h->h_status);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1603,10 +1893,24 @@ void rvl_destroy(rvl_t *h)
 
 const char *rvl_last_error(const rvl_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+// a multi-device handle replicates the staging calls on every child (the epoch data and the model
+// table are small and read-only: SURVEY.md 8(e))
+#define RVL_FANOUT(h, call)                                                                      \
+    do {                                                                                         \
+        if (!(h)->kids.empty()) {                                                                \
+            for (rvl_t *k : (h)->kids) {                                                         \
+                const int rc_ = (call);                                                          \
+                if (rc_) return multi_fail(h, k, rc_);                                           \
+            }                                                                                    \
+            return RVL_OK;                                                                       \
+        }                                                                                        \
+    } while (0)
+
 int rvl_set_data(rvl_t *h, const double *t, const double *rv, const double *err,
                  const int32_t *inst, int32_t n, int32_t n_inst)
 {
     if (!h) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_set_data(k, t, rv, err, inst, n, n_inst));
     if (!t || !rv || !err || !inst) return fail(h, RVL_EINVAL, "NULL data pointer");
     if (n <= 0) return fail(h, RVL_EINVAL, "n must be positive");
     if (n_inst <= 0 || n_inst > RVL_MAX_INST)
@@ -1624,6 +1928,7 @@ int rvl_set_data(rvl_t *h, const double *t, const double *rv, const double *err,
 int rvl_set_linpar(rvl_t *h, int32_t idx, const double *col, int32_t n)
 {
     if (!h) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_set_linpar(k, idx, col, n));
     if (!h->have_data) return fail(h, RVL_ESTATE, "set data first");
     if (idx < 0 || idx >= RVL_MAX_LINPAR || !col || n != h->N)
         return fail(h, RVL_EINVAL, "bad linear-parameter column");
@@ -1637,6 +1942,7 @@ static bool param_ok(const rvl_param &p, int ndim) { return p.slot >= -1 && p.sl
 int rvl_set_model(rvl_t *h, const rvl_model_desc *d)
 {
     if (!h) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_set_model(k, d));
     if (!d) return fail(h, RVL_EINVAL, "desc is NULL");
     if (d->abi_version != RVL_ABI_VERSION) return fail(h, RVL_EINVAL, "abi_version mismatch");
     if (d->ndim < 0 || d->ndim > RVL_MAX_DIM) return fail(h, RVL_EINVAL, "ndim out of range");
@@ -1674,6 +1980,7 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
                    int64_t n_table_doubles)
 {
     if (!h) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_set_priors(k, priors, ndim, tables, n_table_doubles));
     if (!priors || ndim <= 0 || ndim > RVL_MAX_DIM) return fail(h, RVL_EINVAL, "bad priors / ndim");
     for (int i = 0; i < ndim; ++i) {
         const rvl_prior_desc &p = priors[i];
@@ -1700,6 +2007,7 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
 int rvl_set_option(rvl_t *h, const char *name, int64_t value)
 {
     if (!h || !name) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_set_option(k, name, value));
     const std::string n(name);
     if (n == "variant") { if (value < 0 || value > 1) return fail(h, RVL_EINVAL, "variant in {0,1}"); h->opt_variant = (int)value; }
     else if (n == "slices") h->opt_slices = (int)std::max<int64_t>(0, value);
@@ -1714,7 +2022,8 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
     else if (n == "prepare") h->opt_prepare = value != 0;
     else if (n == "trace") h->opt_trace = value != 0;
     else if (n == "setup_items") h->opt_setup_items = value != 0;
-    else if (n == "ilp") { if (value != 1 && value != 2) return fail(h, RVL_EINVAL, "ilp in {1,2}"); h->opt_ilp = (int)value; }
+    else if (n == "gather_timeout_ms") h->opt_gather_timeout_ms = std::max<int64_t>(1, value);
+    else if (n == "ilp") { if (value < 1 || value > 4) return fail(h, RVL_EINVAL, "ilp in {1,2,3,4}"); h->opt_ilp = (int)value; }
     else return fail(h, RVL_EINVAL, "unknown option " + n);
     return RVL_OK;
 }
@@ -1722,6 +2031,7 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
 int rvl_loglike_dev(rvl_t *h, const double *dTheta, int64_t B, double *dlnL, void *stream)
 {
     if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "device-pointer entry points need a single-device handle");
     if (B < 0 || (B > 0 && (!dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
     DevGuard g(h->device);
     return enqueue_loglike(h, nullptr, const_cast<double *>(dTheta), B, dlnL, (cudaStream_t)stream,
@@ -1733,6 +2043,7 @@ int rvl_loglike_dev_scatter(rvl_t *h, const double *dTheta, int64_t B, double *d
                             void *stream)
 {
     if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "device-pointer entry points need a single-device handle");
     if (B < 0 || (B > 0 && (!dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
     if (n_peers < 0 || n_peers > RVL_MAX_PEERS || (n_peers > 0 && !peer_ptrs) || offset < 0)
         return fail(h, RVL_EINVAL, "bad peer list");
@@ -1750,6 +2061,7 @@ int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dl
                            int64_t flag_offset, uint64_t seq, void *stream)
 {
     if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "device-pointer entry points need a single-device handle");
     if (B <= 0 || !dTheta || !dlnL) return fail(h, RVL_EINVAL, "bad arguments");
     if (n_peers < 1 || n_peers > RVL_MAX_PEERS || !peer_ptrs || offset < 0 || rank < 0 ||
         rank >= n_peers || flag_offset < 0 || seq == 0)
@@ -1766,7 +2078,8 @@ int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dl
                              h->opt_timing != 0, &po);
     if (rc) return rc;
     wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const unsigned long long *>(po.ptr[rank]) + flag_offset, n_peers, seq);
+        reinterpret_cast<const unsigned long long *>(po.ptr[rank]) + flag_offset, n_peers, seq,
+        (unsigned long long)h->opt_gather_timeout_ms * 1000000ull, h->d_status);
     CU(h, cudaGetLastError());
     ++h->launches;
     return RVL_OK;
@@ -1775,6 +2088,7 @@ int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dl
 int rvl_transform_dev(rvl_t *h, const double *dU, int64_t B, double *dTheta, void *stream)
 {
     if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "device-pointer entry points need a single-device handle");
     if (B < 0 || (B > 0 && (!dU || !dTheta))) return fail(h, RVL_EINVAL, "bad arguments");
     DevGuard g(h->device);
     return enqueue_transform(h, dU, B, dTheta, (cudaStream_t)stream);
@@ -1784,6 +2098,7 @@ int rvl_transform_loglike_dev(rvl_t *h, const double *dU, int64_t B, double *dTh
                               void *stream)
 {
     if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "device-pointer entry points need a single-device handle");
     if (B < 0 || (B > 0 && (!dU || !dTheta || !dlnL))) return fail(h, RVL_EINVAL, "bad arguments");
     if (h->have_model && h->have_priors && h->prior_ndim != h->model.ndim)
         return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
@@ -1795,127 +2110,82 @@ int rvl_loglike(rvl_t *h, const double *Theta, int64_t B, double *lnL)
 {
     if (!h) return RVL_EINVAL;
     if (B < 0 || (B > 0 && (!Theta || !lnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->kids.empty()) return multi_rows(h, Theta, nullptr, nullptr, lnL, B, /*mode=*/0);
     if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
     if (B == 0) return RVL_OK;
     DevGuard g(h->device);
-    int rc = ensure_io(h, B);
+    HostCall hc;
+    int rc = loglike_begin(h, Theta, B, lnL, hc);
     if (rc) return rc;
-    // A pinned theta is read in place (zero-copy): the likelihood kernel reads every row ONCE, with
-    // one coalesced warp read (the setup item of a split point, or the point's only item), so the
-    // PCIe transfer overlaps the arithmetic instead of preceding it.  When the epoch axis needs
-    // several resident ranges every range would read the row: theta is then staged by a DMA copy.
-    // Pageable buffers (numpy arrays) pass through pinned bounce buffers.  lnL is written in place.
-    const size_t nb = (size_t)B * h->model.ndim * sizeof(double);
-    Plan pl;
-    if (h->cols_dirty) { rc = upload_columns(h); if (rc) return rc; }
-    rc = make_plan(h, B, pl);
-    if (rc) return rc;
-    const bool once = pl.Sm == 1 && (h->opt_setup_items || pl.n_split == 0) && !h->opt_prepare;
-    const void *src;
-    bool src_pinned;
-    rc = bounce_in(h, Theta, nb, &src, &src_pinned);
-    if (rc) return rc;
-    double *th_dev = (src_pinned && (h->opt_zero_copy > 1 || (h->opt_zero_copy == 1 && once)))
-                         ? (double *)pinned_alias(h, src) : nullptr;
-    const bool via_prepare = th_dev != nullptr && !once;
-    if (!th_dev) {
-        th_dev = h->d_theta;
-        if (nb) CU(h, cudaMemcpyAsync(h->d_theta, src, nb, cudaMemcpyHostToDevice, h->stream));
-    }
-    void *out_host;
-    bool out_copy;
-    rc = bounce_out(h, lnL, (size_t)B * sizeof(double), &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
-    if (rc) return rc;
-    double *out_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
-    rc = enqueue_loglike(h, nullptr, th_dev, B, out_dev ? out_dev : h->d_lnl, h->stream,
-                         h->opt_timing != 0, nullptr, via_prepare);
-    if (rc) return rc;
-    if (!out_dev)
-        CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    if (out_dev && out_copy) memcpy(lnL, out_host, (size_t)B * sizeof(double));
-    return finish_timing(h);
+    return hostcall_end(h, hc);
 }
 
 int rvl_transform(rvl_t *h, const double *U, int64_t B, double *Theta)
 {
     if (!h) return RVL_EINVAL;
     if (B < 0 || (B > 0 && (!U || !Theta))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->kids.empty()) return multi_rows(h, nullptr, U, Theta, nullptr, B, /*mode=*/1);
     if (!h->have_priors) return fail(h, RVL_ESTATE, "set priors first");
     if (B == 0) return RVL_OK;
     DevGuard g(h->device);
-    int rc = ensure_io(h, B);
+    HostCall hc;
+    int rc = transform_begin(h, U, B, Theta, hc);
     if (rc) return rc;
-    const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
-    // elementwise and HBM-bound on the device, PCIe-bound here: U is read and theta written in
-    // place through pinned memory (the caller's, or the bounce buffers for pageable arrays)
-    const void *src;
-    bool src_pinned;
-    rc = bounce_in(h, U, nb, &src, &src_pinned);
-    if (rc) return rc;
-    const double *u_dev = src_pinned ? (const double *)pinned_alias(h, src) : nullptr;
-    if (!u_dev) {
-        CU(h, cudaMemcpyAsync(h->d_u, src, nb, cudaMemcpyHostToDevice, h->stream));
-        u_dev = h->d_u;
-    }
-    void *out_host;
-    bool out_copy;
-    rc = bounce_out(h, Theta, nb, &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
-    if (rc) return rc;
-    double *th_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
-    rc = enqueue_transform(h, u_dev, B, th_dev ? th_dev : h->d_theta, h->stream);
-    if (rc) return rc;
-    if (!th_dev)
-        CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    if (th_dev && out_copy) memcpy(Theta, out_host, nb);
-    return RVL_OK;
+    return hostcall_end(h, hc);
 }
 
 int rvl_transform_loglike(rvl_t *h, const double *U, int64_t B, double *Theta, double *lnL)
 {
     if (!h) return RVL_EINVAL;
     if (B < 0 || (B > 0 && (!U || !lnL))) return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->kids.empty()) return multi_rows(h, nullptr, U, Theta, lnL, B, /*mode=*/2);
     if (!h->have_data || !h->have_model || !h->have_priors)
         return fail(h, RVL_ESTATE, "set data, model and priors first");
     if (h->prior_ndim != h->model.ndim) return fail(h, RVL_ESTATE, "priors and model disagree on ndim");
     if (B == 0) return RVL_OK;
     DevGuard g(h->device);
+    HostCall hc;
+    int rc = transform_loglike_begin(h, U, B, Theta, lnL, hc);
+    if (rc) return rc;
+    return hostcall_end(h, hc);
+}
+
+/* per-rank host-buffer form of the fused all-gather (one process per GPU): this rank's rows of
+ * theta in host memory in, the gathered lnL of ALL ranks in host memory out */
+int rvl_loglike_gather(rvl_t *h, const double *Theta, int64_t B, double *lnL_all,
+                       const uint64_t *peer_ptrs, int32_t n_peers, int32_t rank,
+                       int64_t flag_offset, uint64_t seq)
+{
+    if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "not available on a multi-device handle");
+    if (B <= 0 || !Theta || !lnL_all) return fail(h, RVL_EINVAL, "bad arguments");
+    if (n_peers < 1 || n_peers > RVL_MAX_PEERS || !peer_ptrs || rank < 0 || rank >= n_peers ||
+        flag_offset < (int64_t)n_peers * B || seq == 0)
+        return fail(h, RVL_EINVAL, "bad peer list");
+    if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
+    PeerOut po{};
+    po.n = n_peers;
+    po.offset = (long long)rank * B;
+    po.flag_off = flag_offset;
+    po.seq = seq;
+    po.rank = rank;
+    for (int r = 0; r < n_peers; ++r) po.ptr[r] = reinterpret_cast<double *>(peer_ptrs[r]);
+    DevGuard g(h->device);
+    HostCall hc;
     int rc = ensure_io(h, B);
     if (rc) return rc;
-    const size_t nb = (size_t)B * h->prior_ndim * sizeof(double);
-    // pinned buffers (the caller's, or the bounce buffers for pageable arrays) are read / written
-    // in place by the prepare pass and the kernels
-    const void *src;
-    bool src_pinned;
-    rc = bounce_in(h, U, nb, &src, &src_pinned);
+    rc = loglike_begin(h, Theta, B, nullptr, hc, &po, h->d_lnl);
     if (rc) return rc;
-    const double *u_dev = src_pinned ? (const double *)pinned_alias(h, src) : nullptr;
-    if (!u_dev) {
-        CU(h, cudaMemcpyAsync(h->d_u, src, nb, cudaMemcpyHostToDevice, h->stream));
-        u_dev = h->d_u;
-    }
-    void *th_host = nullptr, *out_host = nullptr;
-    bool th_copy = false, out_copy = false;
-    if (Theta) {
-        rc = bounce_out(h, Theta, nb, &h->pin_out2, &h->cap_pin_out2, &th_host, &th_copy);
-        if (rc) return rc;
-    }
-    rc = bounce_out(h, lnL, (size_t)B * sizeof(double), &h->pin_out, &h->cap_pin_out, &out_host, &out_copy);
+    wait_flags_kernel<<<1, 32, 0, h->stream>>>(
+        reinterpret_cast<const unsigned long long *>(po.ptr[rank]) + flag_offset, n_peers, seq,
+        (unsigned long long)h->opt_gather_timeout_ms * 1000000ull, h->d_status);
+    CU(h, cudaGetLastError());
+    ++h->launches;
+    CU(h, cudaMemcpyAsync(lnL_all, po.ptr[rank], (size_t)n_peers * (size_t)B * sizeof(double),
+                          cudaMemcpyDeviceToHost, h->stream));
+    rc = hostcall_end(h, hc);
     if (rc) return rc;
-    double *th_dev = th_host ? (double *)pinned_alias(h, th_host) : nullptr;
-    double *out_dev = out_host ? (double *)pinned_alias(h, out_host) : nullptr;
-    rc = enqueue_loglike(h, u_dev, th_dev ? th_dev : h->d_theta, B, out_dev ? out_dev : h->d_lnl,
-                         h->stream, h->opt_timing != 0);
-    if (rc) return rc;
-    if (Theta && !th_dev)
-        CU(h, cudaMemcpyAsync(Theta, h->d_theta, nb, cudaMemcpyDeviceToHost, h->stream));
-    if (!out_dev)
-        CU(h, cudaMemcpyAsync(lnL, h->d_lnl, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    if (th_dev && th_copy) memcpy(Theta, th_host, nb);
-    if (out_dev && out_copy) memcpy(lnL, out_host, (size_t)B * sizeof(double));
-    return finish_timing(h);
+    return check_gather_status(h);
 }
 
 int rvl_trueanomaly(rvl_t *h, const double *M, int32_t n, double ecc, double *nu,
@@ -1924,31 +2194,47 @@ int rvl_trueanomaly(rvl_t *h, const double *M, int32_t n, double ecc, double *nu
     if (!h) return RVL_EINVAL;
     if (n < 0 || (n > 0 && (!M || !nu)) || niterationmax < 1) return fail(h, RVL_EINVAL, "bad arguments");
     if (n == 0) return 0;
+    if (!h->kids.empty()) return rvl_trueanomaly(h->kids[0], M, n, ecc, nu, niterationmax, tol);
     DevGuard g(h->device);
     double *dM = nullptr, *dnu = nullptr;
     int *dcap = nullptr;
-    CU(h, cudaMalloc(&dM, sizeof(double) * (size_t)n));
-    CU(h, cudaMalloc(&dnu, sizeof(double) * (size_t)n));
-    CU(h, cudaMalloc(&dcap, sizeof(int)));
-    CU(h, cudaMemsetAsync(dcap, 0, sizeof(int), h->stream));
-    CU(h, cudaMemcpyAsync(dM, M, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    const int tb = 128;
-    trueanomaly_kernel<<<(n + tb - 1) / tb, tb, 0, h->stream>>>(dM, n, ecc, dnu, niterationmax, tol, dcap);
-    ++h->launches;
     int cap = 0;
-    cudaError_t e1 = cudaGetLastError();
-    cudaMemcpyAsync(nu, dnu, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(&cap, dcap, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    // one exit: the three scratch buffers are released whatever fails
+    cudaError_t e = cudaMalloc(&dM, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&dnu, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&dcap, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(dcap, 0, sizeof(int), h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dM, M, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const int tb = 128;
+        trueanomaly_kernel<<<(n + tb - 1) / tb, tb, 0, h->stream>>>(dM, n, ecc, dnu, niterationmax, tol, dcap);
+        ++h->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nu, dnu, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cap, dcap, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(h->stream);
     cudaFree(dM); cudaFree(dnu); cudaFree(dcap);
-    if (e1 != cudaSuccess) return fail(h, RVL_ECUDA, cudaGetErrorString(e1));
-    if (e2 != cudaSuccess) return fail(h, RVL_ECUDA, cudaGetErrorString(e2));
+    if (e != cudaSuccess) return fail(h, RVL_ECUDA, std::string("rvl_trueanomaly: ") + cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(h, RVL_ECUDA, std::string("rvl_trueanomaly: ") + cudaGetErrorString(e2));
     return cap ? -1 : 0;  // same 0 / -1 convention as trueanomaly.c:32-40
 }
 
 int rvl_counters(rvl_t *h, rvl_counters_t *out)
 {
     if (!h || !out) return RVL_EINVAL;
+    if (!h->kids.empty()) {  // sums over the devices
+        rvl_counters_t acc{};
+        for (rvl_t *k : h->kids) {
+            rvl_counters_t c{};
+            const int rc = rvl_counters(k, &c);
+            if (rc) return multi_fail(h, k, rc);
+            acc.n_points += c.n_points; acc.n_solves += c.n_solves; acc.n_newton_iters += c.n_newton_iters;
+            acc.n_cap_hits += c.n_cap_hits; acc.n_invalid += c.n_invalid;
+        }
+        *out = acc;
+        return RVL_OK;
+    }
     DevGuard g(h->device);
     unsigned long long c[3] = {0, 0, 0};
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1961,6 +2247,7 @@ int rvl_counters(rvl_t *h, rvl_counters_t *out)
 int rvl_reset_counters(rvl_t *h)
 {
     if (!h) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_reset_counters(k));
     DevGuard g(h->device);
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaMemset(h->d_counters, 0, 3 * sizeof(unsigned long long)));
@@ -1971,6 +2258,17 @@ int rvl_reset_counters(rvl_t *h)
 int rvl_last_kernel_ms(rvl_t *h, double *ms)
 {
     if (!h || !ms) return RVL_EINVAL;
+    if (!h->kids.empty()) {  // the devices run concurrently: the call's kernel time is the longest
+        double worst = 0.0;
+        for (rvl_t *k : h->kids) {
+            double v = 0.0;
+            const int rc = rvl_last_kernel_ms(k, &v);
+            if (rc) return multi_fail(h, k, rc);
+            worst = std::max(worst, v);
+        }
+        *ms = worst;
+        return RVL_OK;
+    }
     if (h->timing_pending) {  // *_dev launches: wait for the kernel's end event
         DevGuard g(h->device);
         CU(h, cudaEventSynchronize(h->ev1));
@@ -1985,12 +2283,53 @@ int rvl_launch_count(rvl_t *h, uint64_t *n)
 {
     if (!h || !n) return RVL_EINVAL;
     *n = h->launches;
+    for (rvl_t *k : h->kids) *n += k->launches;
     return RVL_OK;
+}
+
+/* Recovery after a faulted or aborted launch: the work / arrival counters and the ready stamps
+ * re-arm themselves only when a launch runs to its end; this puts them back to the state of a
+ * fresh handle (the stream is drained first).  Also clears a recorded all-gather timeout. */
+int rvl_reset(rvl_t *h)
+{
+    if (!h) return RVL_EINVAL;
+    RVL_FANOUT(h, rvl_reset(k));
+    DevGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaGetLastError();  // a sticky launch failure is reported by the next call, not swallowed here
+    CU(h, cudaMemset(h->d_work, 0, sizeof(unsigned) * (size_t)(h->sm_count + 1)));
+    if (h->d_arrive) CU(h, cudaMemset(h->d_arrive, 0, (size_t)h->cap_arrive * sizeof(int)));
+    if (h->d_ready) CU(h, cudaMemset(h->d_ready, 0, (size_t)h->cap_ready * sizeof(unsigned)));
+    h->seq = 0;
+    h->timing_pending = false;
+    if (h->h_status) { h->h_status[0] = 0; h->h_status[1] = 0; }
+    return RVL_OK;
+}
+
+/* 0 when no bounded wait of the fused all-gather has expired on this handle since the last check;
+ * RVL_EPEER (message: the exchange number and the missing ranks) otherwise.  For the asynchronous
+ * rvl_loglike_dev_gather: call it after synchronising the stream. */
+int rvl_gather_status(rvl_t *h)
+{
+    if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return RVL_OK;
+    return check_gather_status(h);
 }
 
 int rvl_fp64_peak(rvl_t *h, double *tflops)
 {
     if (!h || !tflops) return RVL_EINVAL;
+    if (!h->kids.empty()) {  // sum over the devices
+        double tot = 0.0;
+        for (rvl_t *k : h->kids) {
+            double v = 0.0;
+            const int rc = rvl_fp64_peak(k, &v);
+            if (rc) return multi_fail(h, k, rc);
+            tot += v;
+        }
+        *tflops = tot;
+        return RVL_OK;
+    }
     DevGuard g(h->device);
     const int blocks = h->sm_count, tb = 1024, iters = 4000;
     double *out = nullptr;
@@ -2019,6 +2358,7 @@ int rvl_read_trace(rvl_t *h, uint64_t *out, int32_t cap_rows, int32_t *rows)
 {
     if (!h || !out || !rows) return RVL_EINVAL;
     *rows = 0;
+    if (!h->kids.empty()) return rvl_read_trace(h->kids[0], out, cap_rows, rows);
     if (!h->d_trace || h->trace_rows <= 0) return fail(h, RVL_ESTATE, "no trace recorded (option \"trace\")");
     if (cap_rows < h->trace_rows) return fail(h, RVL_EINVAL, "trace buffer too small");
     DevGuard g(h->device);
@@ -2035,7 +2375,7 @@ int rvl_plan_describe(const int32_t *in, int64_t B, int64_t *out, int32_t cap)
     pi.Ctot = in[0]; pi.ncol = in[1]; pi.wstride = in[2]; pi.wblock = in[2]; pi.U = in[3]; pi.W = in[4];
     pi.sm_count = in[5]; pi.smem_optin = in[6]; pi.sched = in[7]; pi.slices = in[8];
     pi.items_per_warp = in[9]; pi.min_chunks = in[10]; pi.phase_items = in[11]; pi.max_split = in[12];
-    if (pi.Ctot < 1 || pi.U < 1 || pi.U > 2 || pi.W < 1 || pi.sm_count < 1 || B < 1) return RVL_EINVAL;
+    if (pi.Ctot < 1 || pi.U < 1 || pi.U > 4 || pi.W < 1 || pi.sm_count < 1 || B < 1) return RVL_EINVAL;
     Plan pl{};
     if (plan_core(pi, B, pl)) return RVL_EINVAL;
     if (cap < 8 + 5 * pl.nph) return RVL_EINVAL;

@@ -140,3 +140,22 @@ class FusedGatherLikelihood:
                                                      self.rank * rows)
             self.hdls[k].barrier()  # all peers' stores have landed
         return self.bufs[k][: self.world * rows]
+
+    def evaluate_local_host(self, theta_host, out_all_host):
+        """
+        The same exchange for HOST buffers in one library call (``rvl_loglike_gather``):
+        ``theta_host[rows, ndim]`` (numpy, page-locked for the in-place read) ->
+        ``out_all_host[world * rows]`` (numpy) holding every rank's lnL.  Synchronous.
+        """
+        rows = theta_host.shape[0]
+        if self.signal != "flags":
+            raise ValueError("the host-buffer form uses the completion flags")
+        if rows != self.max_rows:
+            # the completion slots sit behind world * max_rows values: a smaller block would leave a
+            # gap between the ranks' blocks, which the one D2H copy of the call does not skip
+            raise ValueError("evaluate_local_host needs rows == max_rows")
+        k = self.turn
+        self.turn ^= 1
+        self.seq[k] += 1
+        return self.model.log_likelihood_gather_host(theta_host, out_all_host, self.ptrs[k],
+                                                     self.rank, self.flag_off, self.seq[k])

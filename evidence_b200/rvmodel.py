@@ -90,13 +90,15 @@ class RVModel(BaseModel):
     Drop-in for evidence.rvmodel.RVModel whose likelihood runs on a B200.
 
     Extra keyword arguments (all optional): ``device`` (CUDA device index, default: current),
+    ``devices`` (a list of device indices, or ``"all"``: ONE model over several GPUs of the box --
+    ``rvl_create_multi``; every host-buffer batch call then splits its rows over them),
     ``linpar_dict`` (name -> per-epoch array, the reference's ``self.linpar_dict``,
     evidence/rvmodel/__init__.py:131-136, 210-212), ``tol`` / ``itmax`` (Newton tolerance and
     cap; the reference hard-codes 1e-4 and 10000, :466, :491).
     """
 
     def __init__(self, fixedpardict, datadict, parnames, device=None, linpar_dict=None,
-                 tol=1.0e-4, itmax=10000):
+                 tol=1.0e-4, itmax=10000, devices=None):
         super().__init__(fixedpardict, datadict, parnames)
         # structure from the free names only (:118-139)
         self.nplanets = sum("k1" in p for p in self.parnames)
@@ -118,7 +120,14 @@ class RVModel(BaseModel):
         self._lib = _abi.load()
         self._h = c_void_p()
         self.device_index = None if device is None else int(device)  # None: the current device
-        rc = self._lib.rvl_create(byref(self._h), -1 if device is None else int(device))
+        if devices is not None:
+            if device is not None:
+                raise ValueError("give either device or devices")
+            devs = [] if devices == "all" else [int(d) for d in devices]
+            arr = (c_int32 * max(1, len(devs)))(*devs)
+            rc = self._lib.rvl_create_multi(byref(self._h), arr if devs else None, len(devs))
+        else:
+            rc = self._lib.rvl_create(byref(self._h), -1 if device is None else int(device))
         if rc != 0:
             msg = self._lib.rvl_last_error(None).decode()
             raise DeviceError(f"rvl_create failed ({_abi.RVL_ERRORS.get(rc, rc)}): {msg}")
@@ -241,6 +250,29 @@ class RVModel(BaseModel):
             self._h, c_void_p(theta.data_ptr()), B, c_void_p(out.data_ptr()), arr, len(peer_ptrs),
             int(rank), int(offset), int(flag_offset), int(seq), c_void_p(stream)))
         return out
+
+    def log_likelihood_gather_host(self, X, out_all, peer_ptrs, rank, flag_offset, seq):
+        """
+        Per-rank host-buffer form of the fused all-gather (``rvl_loglike_gather``): this rank's rows
+        ``X[B, ndim]`` (host, ideally page-locked) in, ``out_all[world * B]`` (host) = lnL of all
+        ranks out.  One synchronous call per step.
+        """
+        B = X.shape[0]
+        arr = (c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        rc = self._lib.rvl_loglike_gather(self._h, X.ctypes.data, B, out_all.ctypes.data, arr,
+                                          len(peer_ptrs), int(rank), int(flag_offset), int(seq))
+        if rc != 0:
+            self._check(rc)
+        return out_all
+
+    def device_count(self):
+        n = c_int32()
+        self._check(self._lib.rvl_device_count(self._h, byref(n)))
+        return n.value
+
+    def reset(self):
+        """Re-arm the handle after a faulted launch (``rvl_reset``)."""
+        self._check(self._lib.rvl_reset(self._h))
 
     # ------------------------------------------------------------------ priors
     def set_priors(self, priordict):

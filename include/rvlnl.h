@@ -59,6 +59,7 @@ extern "C" {
 #define RVL_ECUDA (-3)   /* CUDA runtime error (see rvl_last_error)        */
 #define RVL_ESTATE (-4)  /* call order: data/model/priors not yet set      */
 #define RVL_ENOMEM (-5)
+#define RVL_EPEER (-6)   /* fused all-gather: a peer rank never signalled (bounded wait expired) */
 
 typedef struct rvl_handle rvl_t;
 
@@ -144,7 +145,22 @@ typedef struct {
 int rvl_abi_version(void);
 /* device < 0: use the current CUDA device */
 int rvl_create(rvl_t **out, int device);
+/* One handle over several GPUs of the box, for a single-process caller (a ctypes consumer bound as
+ * in INTEGRATION.md gets the whole box through the SAME calls): the staging calls are replicated on
+ * every device, and every host-buffer hot call (rvl_transform / rvl_loglike /
+ * rvl_transform_loglike) splits its B rows into contiguous blocks -- device i of n owns rows
+ * [i*ceil(B/n), min(B, (i+1)*ceil(B/n))), the partition the samplers' MPI ranks use
+ * (evidence/ultranest/__init__.py:21-29) -- launches all devices from the calling thread and
+ * returns when all have finished.  Page-locked caller buffers are read and written in place by all
+ * devices, so the gathered lnL vector is simply the caller's buffer.  devices == NULL /
+ * n_devices == 0: every device of the box.  The *_dev entry points need a single-device handle. */
+int rvl_create_multi(rvl_t **out, const int32_t *devices, int32_t n_devices);
+/* number of devices behind the handle (1 for rvl_create) */
+int rvl_device_count(rvl_t *h, int32_t *n);
 void rvl_destroy(rvl_t *h);
+/* back to the state of a fresh handle after a faulted / aborted launch (work counters, arrival
+ * counters and ready stamps only re-arm themselves when a launch runs to its end) */
+int rvl_reset(rvl_t *h);
 /* h may be NULL: returns the last error of the calling thread (rvl_create failures) */
 const char *rvl_last_error(const rvl_t *h);
 
@@ -168,7 +184,7 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
  *               axis needs several resident ranges; 2: in place even then (through the
  *               once-per-point pass); 0: stage everything with cudaMemcpyAsync
  *   "variant"   0 optimised kernel (default), 1 conservative cross-check (IEEE division, full sin/cos)
- *   "ilp"       epochs per lane in flight, 1 or 2 (default 2)
+ *   "ilp"       epochs per lane in flight, 1..4 (default 2)
  *   "sched"     1 (default): graded work list -- whole points first, then the points at the end of the
  *               batch cut into 2, 4, .. "max_split" (8) sub-slices with about "phase_items" (200)
  *               percent of one item per warp in each phase, so that all warps run dry together;
@@ -177,6 +193,7 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
  *               derived once, by setup items at the head of the kernel's own work list
  *   "prepare"   1: per-point constants from the once-per-point pass even without a transform
  *   "trace"     1: per-warp time stamps of the last launch (rvl_read_trace)
+ *   "gather_timeout_ms" bound of the wait for the peers' completion slots in the fused all-gather
  *   "slices", "warps": launch-plan overrides (0 = automatic) */
 int rvl_set_option(rvl_t *h, const char *name, int64_t value);
 
@@ -217,6 +234,19 @@ int rvl_loglike_dev_scatter(rvl_t *h, const double *dTheta, int64_t B, double *d
 int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dlnL,
                            const uint64_t *peer_ptrs, int32_t n_peers, int32_t rank, int64_t offset,
                            int64_t flag_offset, uint64_t seq, void *stream);
+
+/* The same exchange for HOST buffers, one call per rank and step (what a sampler running one
+ * process per GPU does where UltraNest's MPI mode gathers the ranks' likelihood values,
+ * evidence/ultranest/__init__.py:21-29): this rank's B rows of theta (page-locked: read in place by
+ * the kernel) -> lnL of ALL ranks, lnL_all[n_peers * B] in host memory, rank r's block at r*B.
+ * peer_ptrs / flag_offset / seq as above; every rank passes the same B.  Synchronous.  A peer that
+ * never signals makes the call fail with RVL_EPEER after "gather_timeout_ms" (default 10000)
+ * instead of hanging the stream. */
+int rvl_loglike_gather(rvl_t *h, const double *Theta, int64_t B, double *lnL_all,
+                       const uint64_t *peer_ptrs, int32_t n_peers, int32_t rank,
+                       int64_t flag_offset, uint64_t seq);
+/* after synchronising the stream of an rvl_loglike_dev_gather: RVL_EPEER if its bounded wait expired */
+int rvl_gather_status(rvl_t *h);
 
 /* ---- the reference's own native FFI, on the device (trueanomaly.h:4) ----- */
 /* Same contract as the reference symbol except: returns -1 when ANY element hit the cap

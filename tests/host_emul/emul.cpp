@@ -64,6 +64,15 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
                 all_medium = all_medium && (h < kHiMedium);
                 any_big = any_big || !(abs_hi(E[u][l]) < kHiTrigMax);
             }
+        bool all_final = true;
+        const int tol_hi = rvl::hi32(tol);
+        for (int u = 0; u < U; ++u)
+            for (int l = 0; l < W; ++l) all_final = all_final && (abs_hi(d[u][l]) < tol_hi);
+        if (all_final && tol_hi < rvl::kHiFinal) {  // the last pass: shorter series, then out
+            ++st.trips_tiny;
+            for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_final(d[u][l], s[u][l], c[u][l]);
+            break;
+        }
         if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(d[u][l], s[u][l], c[u][l]); }
         else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(d[u][l], s[u][l], c[u][l]); }
         else if (!slow && all_medium) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_medium(d[u][l], s[u][l], c[u][l]); }
@@ -79,7 +88,7 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
         bool pa[2][W], any_left = false;
         for (int u = 0; u < U; ++u)
             for (int l = 0; l < W; ++l) {
-                pa[u][l] = fabs(d[u][l]) > tol;
+                pa[u][l] = rvl::abs_gt(d[u][l], rvl::hi32(tol), (uint32_t)rvl::lo32(tol));
                 any_left = any_left || pa[u][l];
             }
         if (trip >= itmax || !any_left) break;
@@ -98,7 +107,7 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
         for (int l = 0; l < W; ++l) {
             iters[u][l] += last[u][l];
             caps[l] += (fabs(d[u][l]) > tol) ? 1 : 0;
-            out[u][l] = rvl::kepler_rv(s[u][l], c[u][l], ec, A, Bs, Ce);
+            out[u][l] = rvl::kepler_rv2(s[u][l], c[u][l], ec, A, Bs, Ce, pc[7]);
         }
 }
 
@@ -127,7 +136,7 @@ bool point_setup(const rvl_model_desc &m, const double *row, double *wc)
         double *pc = wc + p * kPlanetStride;
         pc[0] = 6.283185307179586 / per;
         pc[1] = M0; pc[2] = ec; pc[3] = amp * cw; pc[4] = -((amp * sw) * root);
-        pc[5] = amp * (ecc * cw); pc[6] = par_of(pl.epoch, row);
+        pc[5] = amp * (ecc * cw); pc[6] = par_of(pl.epoch, row); pc[7] = -(pc[3] * ec);
     }
     double *ic = wc + K * kPlanetStride;
     for (int i = 0; i < m.n_inst; ++i) {
