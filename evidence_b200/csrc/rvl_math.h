@@ -162,23 +162,57 @@ RVL_HD double rcp(double x)
         2.48015872894767294178e-05,    /* 13  C3                      */                         \
         -1.38888888888741095749e-03,   /* 14  C2                      */                         \
         4.16666666666666019037e-02,    /* 15  C1                      */                         \
-        -1.0 / 6.0,                    /* 16                          */                         \
-        -1.0 / 24.0,                   /* 17                          */                         \
-        -1.0 / 5040.0,                 /* 18                          */                         \
-        1.0 / 120.0,                   /* 19                          */                         \
-        1.0 / 40320.0,                 /* 20                          */                         \
-        -1.0 / 720.0,                  /* 21                          */                         \
-        1.0 / 24.0,                    /* 22                          */                         \
-        0.999999                       /* 23  multiplier of the FP64 peak probe */                         \
+        0.999999                       /* 16  multiplier of the FP64 peak probe */                         \
     }
-static const double h_ktab[24] = RVL_K_TABLE;
+// The functions below take the table as their first argument (`kt`): the likelihood kernel
+// loads it ONCE per thread into (uniform) registers with loads the compiler may not
+// rematerialise, so that the Newton loop holds no constant loads at all -- FP64 instructions of
+// sm_100a take register or uniform-register operands only, never a constant-bank address, and
+// ptxas otherwise re-loads each path's coefficients on every pass (18 loads per Kepler solve).
+struct KTab {
+    double v[17];
+    int vz;  // device: an opaque per-thread zero (see RVL_KV); host: unused
+};
+static const KTab h_ktab = {RVL_K_TABLE, 0};
 #if defined(__CUDACC__)
-__constant__ double d_ktab[24] = RVL_K_TABLE;
+__constant__ double d_ktab[17] = RVL_K_TABLE;
+__device__ __forceinline__ KTab load_ktab()
+{
+    KTab k;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) k.v[i] = d_ktab[i];
+    // zero in every lane (lanemask_lt < 2^31), but a per-lane value for the assembler
+    asm volatile("mov.u32 %0, %%lanemask_lt;\n\tshr.u32 %0, %0, 31;" : "=r"(k.vz));
+    return k;
+}
+// the same, pinned: the address carries an opaque warp-uniform zero (the SM id is far below 2^16),
+// so the assembler cannot treat the loads as known constants to re-load wherever they are used; they
+// become 17 uniform loads at the top of the kernel whose results stay in uniform registers
+__device__ __forceinline__ KTab load_ktab_pinned()
+{
+    KTab k;
+    unsigned uz;
+    asm volatile("mov.u32 %0, %%smid;\n\tshr.u32 %0, %0, 16;" : "=r"(uz));
+    const size_t base = __cvta_generic_to_constant(d_ktab) + (size_t)uz * 8u;
+#pragma unroll
+    for (int i = 0; i < 17; ++i)
+        asm volatile("ld.const.f64 %0, [%1];" : "=d"(k.v[i]) : "l"(base + 8u * i));
+    // zero in every lane (lanemask_lt < 2^31), but a per-lane value for the assembler
+    asm volatile("mov.u32 %0, %%lanemask_lt;\n\tshr.u32 %0, %0, 31;" : "=r"(k.vz));
+    return k;
+}
 #endif
+#define RVL_K(i) (kt.v[i])
+// A constant that STARTS a Horner chain (or meets a second constant in one instruction) has to sit
+// in an ordinary register -- an FP64 instruction takes at most one uniform operand -- and is
+// cheaper as one 64-bit constant load on the spot than as two moves out of uniform registers.
+// (The index carries an opaque zero that lives in an ordinary register: the load then cannot be
+// turned into a uniform load followed by those two moves.)
 #if defined(__CUDA_ARCH__)
-#define RVL_K(i) (::rvl::d_ktab[i])
+#define RVL_KV(i) \
+    (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(::rvl::d_ktab) + 8 * (i) + kt.vz))
 #else
-#define RVL_K(i) (::rvl::h_ktab[i])
+#define RVL_KV(i) (kt.v[i])
 #endif
 
 // ---- sin & cos of an un-reduced angle ----------------------------------------------------
@@ -188,21 +222,21 @@ __constant__ double d_ktab[24] = RVL_K_TABLE;
 // elsewhere (the first reduction step is exact only while |x| 2/pi < 2^17).
 constexpr double kTrigFastMax = 100000.0;
 
-RVL_HD void sincos_fast(double x, double &s, double &c)
+RVL_HD void sincos_fast(const KTab &kt, double x, double &s, double &c)
 {
-    const double q = fma_(x, RVL_K(0), RVL_K(1));
+    const double q = fma_(x, RVL_K(0), RVL_KV(1));
     const int32_t n = lo32(q);
     const double qf = sub(q, RVL_K(1));
     double r = fma_(-qf, RVL_K(2), x);
     r = fma_(-qf, RVL_K(3), r);
     const double z = mul(r, r);
-    double ps = RVL_K(4);
+    double ps = RVL_KV(4);
     ps = fma_(ps, z, RVL_K(5));
     ps = fma_(ps, z, RVL_K(6));
     ps = fma_(ps, z, RVL_K(7));
     ps = fma_(ps, z, RVL_K(8));
     ps = fma_(ps, z, RVL_K(9));
-    double pc = RVL_K(10);
+    double pc = RVL_KV(10);
     pc = fma_(pc, z, RVL_K(11));
     pc = fma_(pc, z, RVL_K(12));
     pc = fma_(pc, z, RVL_K(13));
@@ -225,27 +259,32 @@ RVL_HD void sincos_fast(double x, double &s, double &c)
 // Writing the update as "old value + small correction" keeps the added rounding error at half
 // an ulp per step however many steps are chained.
 // |d| <= 2^-10 : sin d = d - d^3/6 (next term 7e-18), 1-cos d = d^2/2 - d^4/24.   11 instr.
-RVL_HD void advance_tiny(double d, double &s, double &c)
+// (All the short series below use the leading coefficients of the SAME minimax kernels as
+// sincos_fast -- S1..S3, C1..C3 differ from -1/6, 1/120, .. by < 4e-16 relative, far below what
+// the truncated terms leave -- so that every sin/cos path of the Newton loop draws on one set of
+// 16 constants, which the compiler then keeps resident in uniform registers: no constant loads
+// inside the loop.)
+RVL_HD void advance_tiny(const KTab &kt, double d, double &s, double &c)
 {
     const double d2 = mul(d, d);
-    const double sd = fma_(mul(d, d2), RVL_K(16), d);
-    const double v = mul(d2, fma_(d2, RVL_K(17), 0.5));
+    const double sd = fma_(mul(d, d2), RVL_K(9), d);
+    const double v = mul(d2, fma_(-d2, RVL_K(15), 0.5));
     const double ds = fma_(c, sd, -mul(s, v));
     const double dc = fma_(s, sd, mul(c, v));
     s = add(s, ds);
     c = sub(c, dc);
 }
 // |d| <= 2^-5 : sin d through d^7 (next 8e-20), 1-cos d through d^8 (next 2e-22).   16 instr.
-RVL_HD void advance_small(double d, double &s, double &c)
+RVL_HD void advance_small(const KTab &kt, double d, double &s, double &c)
 {
     const double d2 = mul(d, d);
-    double ps = RVL_K(18);
-    ps = fma_(ps, d2, RVL_K(19));
-    ps = fma_(ps, d2, RVL_K(16));
+    double ps = RVL_KV(7);
+    ps = fma_(ps, d2, RVL_K(8));
+    ps = fma_(ps, d2, RVL_K(9));
     const double sd = fma_(mul(d, d2), ps, d);
-    double pc = RVL_K(20);
-    pc = fma_(pc, d2, RVL_K(21));
-    pc = fma_(pc, d2, RVL_K(22));
+    double pc = RVL_KV(13);
+    pc = fma_(pc, d2, RVL_K(14));
+    pc = fma_(pc, d2, RVL_K(15));
     pc = fma_(pc, d2, -0.5);
     const double v = -mul(d2, pc);
     const double ds = fma_(c, sd, -mul(s, v));
@@ -255,16 +294,16 @@ RVL_HD void advance_small(double d, double &s, double &c)
 }
 // |d| < 0.75 (< pi/4): sin d and 1-cos d from the same minimax kernels as sincos_fast, but with
 // no range reduction and no quadrant logic.  21 FP64 instructions, no integer work.
-RVL_HD void advance_medium(double d, double &s, double &c)
+RVL_HD void advance_medium(const KTab &kt, double d, double &s, double &c)
 {
     const double z = mul(d, d);
-    double ps = RVL_K(4);
+    double ps = RVL_KV(4);
     ps = fma_(ps, z, RVL_K(5));
     ps = fma_(ps, z, RVL_K(6));
     ps = fma_(ps, z, RVL_K(7));
     ps = fma_(ps, z, RVL_K(8));
     ps = fma_(ps, z, RVL_K(9));
-    double pc = RVL_K(10);
+    double pc = RVL_KV(10);
     pc = fma_(pc, z, RVL_K(11));
     pc = fma_(pc, z, RVL_K(12));
     pc = fma_(pc, z, RVL_K(13));
@@ -280,10 +319,10 @@ RVL_HD void advance_medium(double d, double &s, double &c)
 // the LAST pass of a solve: every |d| <= tol (1e-4 in the reference): sin d = d - d^3/6 (next term
 // 8e-23), 1 - cos d = d^2/2 (next term d^4/24 = 4e-18, below half an ulp of the values it is
 // subtracted from).  10 instructions.  Valid for |d| < 2e-4.
-RVL_HD void advance_final(double d, double &s, double &c)
+RVL_HD void advance_final(const KTab &kt, double d, double &s, double &c)
 {
     const double d2 = mul(d, d);
-    const double sd = fma_(mul(d, d2), RVL_K(16), d);
+    const double sd = fma_(mul(d, d2), RVL_K(9), d);
     const double v = mul(0.5, d2);
     const double ds = fma_(c, sd, -mul(s, v));
     const double dc = fma_(s, sd, mul(c, v));
@@ -387,6 +426,78 @@ RVL_HD double log_mantissa(double m, int32_t &half)
     const double R = add(t2, t1);
     const double hfsq = mul(0.5, mul(f, f));
     return sub(f, sub(hfsq, mul(s, add(hfsq, R))));
+}
+
+// ---- exp(x), correctly rounded (double-double inside) ---------------------------------------
+// Only for the once-per-point decode of the log parametrisations (logperiod, logk1:
+// evidence/rvmodel/__init__.py:412-420).  The period is the one hypersensitive input of the path
+// (SURVEY.md 0.5): one ulp of P moves lnL by up to ~1e-8, so exp() has to give THE nearest double,
+// not a <= 1 ulp neighbour.  x = k ln2 + r (three-part ln2, first product exact), t = r / 256,
+// expm1(t) by its Taylor series to t^10 in double-double, eight squarings p <- 2p + p^2, result
+// (1 + p) 2^k.  Relative error ~2^-95: the rounding is correct except within 2^-42 of a tie.
+// ~400 FP64 operations per call; a likelihood item is >= 10^4.
+struct dd {
+    double hi, lo;
+};
+RVL_HD dd dd_two_sum(double a, double b)
+{
+    const double s = add(a, b), bb = sub(s, a);
+    return dd{s, add(sub(a, sub(s, bb)), sub(b, bb))};
+}
+RVL_HD dd dd_quick(double a, double b)  // |a| >= |b|
+{
+    const double s = add(a, b);
+    return dd{s, sub(b, sub(s, a))};
+}
+RVL_HD dd dd_add(dd a, dd b)
+{
+    dd s = dd_two_sum(a.hi, b.hi);
+    const dd t = dd_two_sum(a.lo, b.lo);
+    s.lo = add(s.lo, t.hi);
+    s = dd_quick(s.hi, s.lo);
+    s.lo = add(s.lo, t.lo);
+    return dd_quick(s.hi, s.lo);
+}
+RVL_HD dd dd_mul(dd a, dd b)
+{
+    const double p = mul(a.hi, b.hi);
+    double e = fma_(a.hi, b.hi, -p);
+    e = add(e, add(mul(a.hi, b.lo), mul(a.lo, b.hi)));
+    return dd_quick(p, e);
+}
+RVL_HD double exp_cr(double x)
+{
+    if (!(x > -700.0 && x < 700.0)) return ::exp(x);  // overflow / underflow / nan: library
+    const double kd = sub(fma_(x, 0x1.71547652b82fep+0, 6755399441055744.0), 6755399441055744.0);
+    const int32_t k = (int32_t)kd;
+    // r = x - k ln2: k * L1 is exact (L1 = 32 leading bits of ln2), and so is the difference
+    const double r0 = sub(x, mul(kd, 0x1.62e42fee00000p-1));
+    const double p2 = mul(kd, 0x1.a39ef35793c76p-33);
+    const double p2e = fma_(kd, 0x1.a39ef35793c76p-33, -p2);
+    dd r = dd_two_sum(r0, -p2);
+    r.lo = sub(r.lo, add(p2e, mul(kd, 0x1.cc01f97b57a08p-87)));
+    r = dd_quick(r.hi, r.lo);
+    const dd t = dd{mul(r.hi, 0x1p-8), mul(r.lo, 0x1p-8)};
+    // expm1(t) = t (1 + t (1/2! + t (1/3! + ... + t/11!)))  -> Horner on q = sum_{n>=2} t^(n-2)/n!
+    const double fh[10] = {0x1.0000000000000p-1, 0x1.5555555555555p-3, 0x1.5555555555555p-5,
+                           0x1.1111111111111p-7, 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13,
+                           0x1.a01a01a01a01ap-16, 0x1.71de3a556c734p-19, 0x1.27e4fb7789f5cp-22,
+                           0x1.ae64567f544e4p-26};
+    const double fl[10] = {0.0, 0x1.5555555555555p-57, 0x1.5555555555555p-59, 0x1.1111111111111p-63,
+                           -0x1.f49f49f49f49fp-65, 0x1.a01a01a01a01ap-73, 0x1.a01a01a01a01ap-76,
+                           -0x1.c154f8ddc6c00p-73, 0x1.cbbc05b4fa99ap-76, -0x1.c062e06d1f209p-80};
+    dd q = dd{fh[9], fl[9]};
+    for (int n = 8; n >= 0; --n) q = dd_add(dd_mul(q, t), dd{fh[n], fl[n]});
+    dd p = dd_add(t, dd_mul(dd_mul(t, t), q));  // t + t^2 q
+    for (int i = 0; i < 8; ++i) {               // (1 + p)^2 - 1 = 2p + p^2
+        const dd sq = dd_mul(p, p);
+        p = dd_add(dd{mul(2.0, p.hi), mul(2.0, p.lo)}, sq);
+    }
+    const dd one_p = dd_add(dd{1.0, 0.0}, p);
+    // scale by 2^k through the exponent field (k in [-1010, 1010]: split in two to stay normal)
+    const int32_t k1 = k / 2, k2 = k - k1;
+    const double s1 = from_hilo((k1 + 1023) << 20, 0), s2 = from_hilo((k2 + 1023) << 20, 0);
+    return mul(mul(one_p.hi, s1), s2);
 }
 
 }  // namespace rvl

@@ -38,15 +38,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kPlanetStride = 8;  // doubles per planet in the per-warp constant block
 constexpr int kModelBytes = (int)((sizeof(rvl_model_desc) + 127) / 128 * 128);
 // per-planet constants: 0 nmot, 1 M0, 2 ec, 3 A, 4 Bs, 5 Ce, 6 epoch, 7 -(A ec)
-#ifndef RVL_INT_TOL
-#define RVL_INT_TOL 1   // |d| > tol on the integer pipe
-#endif
-#ifndef RVL_KRV2
-#define RVL_KRV2 1      // kepler_rv2: A (c - ec) from the prepared -(A ec)
-#endif
-#ifndef RVL_FINAL
-#define RVL_FINAL 1     // shorter series for the last pass of a solve (every |d| <= tol)
-#endif
+
 
 // Peer buffers of the fused all-gather: device pointers into the other ranks' (and our own)
 // gathered lnL vectors (NVLink peer / symmetric memory).  Passed by value.
@@ -214,18 +206,19 @@ __device__ __forceinline__ bool any_big(const double (&E)[U])
 }
 
 // ---- U epochs per lane x one planet: Kepler solves + RV terms -------------------------------
-// VARIANT 0: optimised (reciprocal-multiply Newton step, warp-uniform small-step sin/cos
-//            advance).  VARIANT 1: conservative (IEEE division, full sin/cos every step) — kept
-//            as the in-product cross-check of the optimisations, selectable with
-//            rvl_set_option("variant", 1).
-// U independent solves per lane (instruction-level parallelism; control flow, votes and constant
-// loads are shared by the U solves).
-// Lanes freeze individually (trueanomaly.c:21: per-element stop): a frozen lane's step is forced
-// to 0, so its E never moves again and `|d| > tol` keeps it inactive without a separate flag.
+// Lanes freeze individually (trueanomaly.c:21: per-element stop): a frozen lane's step is exactly
+// 0, so its E never moves again and `|d| > tol` keeps it inactive without a separate flag.
+// iters[u] counts the Newton steps BEYOND the first (every solve takes at least one: the caller
+// starts the count at one per planet).
+//
+// solve_planet_ref: the plain statement of the loop -- any tolerance, any |M| (libdevice sin/cos
+// when an argument is >= 1e5 or not finite), VARIANT 1 = IEEE division + full sin/cos every step.
+// It is the conservative kernel build (rvl_set_option("variant", 1), the in-product cross-check)
+// and the fallback of the lean loop below.
 template <int VARIANT, int U>
-__device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, double tol,
-                                             int itmax, double (&rv)[U], int (&iters)[U],
-                                             int &caps)
+__device__ __forceinline__ void solve_planet_ref(const rvl::KTab &kt, const double (&t)[U], uint32_t pc, double tol,
+                                                 int itmax, double (&rv)[U], int (&iters)[U],
+                                                 int &caps)
 {
     const double nmot = lds_f64(pc), M0 = lds_f64(pc + 8), ec = lds_f64(pc + 16),
                  epoch = lds_f64(pc + 48);
@@ -248,29 +241,21 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
     const bool slow = __any_sync(kFull, big || !(ec >= -0.99));
     int trip = 0;  // warp-uniform number of Newton steps taken so far
     const int tol_hi = __double2hiint(tol);
-    const unsigned tol_lo = (unsigned)__double2loint(tol);
-#pragma unroll 2
     for (;;) {
-        // warp-wide maximum of the high words of |d|: ONE redux decides the sin/cos path and
-        // (except in a 1e-6-wide band around tol) the loop exit, all on uniform values
         int hmax = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) hmax = max(hmax, abs_hi(d[u]));
         const int wmax = (int)__reduce_max_sync(kFull, (unsigned)hmax);
         // (1) bring (sin E, cos E) up to date with the step d just taken
-        if (VARIANT == 0 && RVL_FINAL && wmax < tol_hi && tol_hi < rvl::kHiFinal) {
+        if (VARIANT == 0 && wmax < kHiTiny) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) rvl::advance_final(d[u], s[u], c[u]);
-            break;  // every |d| < tol: nothing left to iterate (the exit test below, taken early)
-        } else if (VARIANT == 0 && wmax < kHiTiny) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) rvl::advance_tiny(d[u], s[u], c[u]);
+            for (int u = 0; u < U; ++u) rvl::advance_tiny(kt, d[u], s[u], c[u]);
         } else if (VARIANT == 0 && wmax < kHiSmall) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) rvl::advance_small(d[u], s[u], c[u]);
-        } else if (VARIANT == 0 && RVL_MEDIUM && !slow && wmax < kHiMedium) {
+            for (int u = 0; u < U; ++u) rvl::advance_small(kt, d[u], s[u], c[u]);
+        } else if (VARIANT == 0 && !slow && wmax < kHiMedium) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) rvl::advance_medium(d[u], s[u], c[u]);
+            for (int u = 0; u < U; ++u) rvl::advance_medium(kt, d[u], s[u], c[u]);
         } else if (slow || (trip > 2 && any_big<U>(E))) {
             // |E| can only leave the fast range after >= 3 Newton steps (|step| <= 100 |f|)
 #pragma unroll
@@ -281,13 +266,12 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < U; ++u) rvl::sincos_fast(E[u], s[u], c[u]);
+            for (int u = 0; u < U; ++u) rvl::sincos_fast(kt, E[u], s[u], c[u]);
         }
         // (2) which lanes still iterate (trueanomaly.c:21); the cap (:32-33) bounds the loop
         bool pa[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            pa[u] = (VARIANT == 0 && RVL_INT_TOL) ? rvl::abs_gt(d[u], tol_hi, tol_lo) : (fabs(d[u]) > tol);
+        for (int u = 0; u < U; ++u) pa[u] = fabs(d[u]) > tol;
         if (trip >= itmax || wmax < tol_hi) break;  // high word below tol's: every |d| < tol
         if (wmax == tol_hi) {                       // rare tie on the high word: exact vote
             bool any_left = false;
@@ -302,27 +286,142 @@ __device__ __forceinline__ void solve_planet(const double (&t)[U], uint32_t pc, 
             double En;
             if (VARIANT == 0) {
                 rvl::newton_step(E[u], s[u], c[u], M[u], ec, En);
-                En = pa[u] ? En : E[u];
-                d[u] = rvl::sub(En, E[u]);  // exact
             } else {
                 const double f = rvl::sub(rvl::sub(E[u], rvl::mul(ec, s[u])), M[u]);
                 const double fp = rvl::sub(1.0, rvl::mul(ec, c[u]));
                 En = rvl::sub(E[u], __ddiv_rn(f, fp));
-                En = pa[u] ? En : E[u];
-                d[u] = rvl::sub(En, E[u]);  // exact
             }
+            En = pa[u] ? En : E[u];
+            d[u] = rvl::sub(En, E[u]);  // exact
             E[u] = En;
             last[u] = pa[u] ? trip : last[u];
         }
     }
     const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
-    const double mAec = (VARIANT == 0 && RVL_KRV2) ? lds_f64(pc + 56) : 0.0;
+    const double mAec = lds_f64(pc + 56);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        iters[u] += last[u];
+        iters[u] += last[u] - 1;
         caps += (fabs(d[u]) > tol) ? 1 : 0;
-        rv[u] = (VARIANT == 0 && RVL_KRV2) ? rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec)
-                                           : rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce);
+        rv[u] = VARIANT == 0 ? rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec)
+                             : rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce);
+    }
+}
+
+// The lean loop (VARIANT 0), for the reference tolerance and |M| < 1e5 -- everything a sampler
+// ever asks for; anything else restarts in solve_planet_ref above (a cold, warp-uniform branch), so
+// that the hot loop holds no call and no libdevice code.
+// The cost of this loop is its TOTAL instruction count, not only its FP64 count: measured on B200
+// (profiles/r2_*), cycles per solve = 2.0 x FP64 instructions + 0.84 x all other instructions.
+// So, beyond the arithmetic of rvl_math.h:
+//   * pass 1 (full sin/cos of M, every lane active) is peeled: no path selection, no freeze;
+//   * the warp-wide maximum of |d| comes from ONE FMNMX with |.| modifiers on the high words read
+//     as floats (they order like the doubles) and ONE redux to a uniform register;
+//   * path selection is a two-level tree ordered by frequency; `wmax < tol` picks the short last
+//     pass and leaves (a tie of the high words just runs one more, idle, pass);
+//   * a lane freezes by zeroing the 20-bit seed of its reciprocal (ONE select on the high word):
+//     r = 0 -> E' = fma(-f, 0, E) = E, d = 0, with no 64-bit select on E;
+//   * iteration counts: one predicated add per step; cap hits are only looked for when the cap
+//     was reached.
+template <int VARIANT, int U>
+__device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (&t)[U], uint32_t pc, double tol,
+                                             int itmax, double (&rv)[U], int (&iters)[U],
+                                             int &caps)
+{
+    if (VARIANT != 0) {
+        solve_planet_ref<VARIANT, U>(kt, t, pc, tol, itmax, rv, iters, caps);
+        return;
+    }
+    const double nmot = lds_f64(pc), M0 = lds_f64(pc + 8), ec = lds_f64(pc + 16),
+                 epoch = lds_f64(pc + 48);
+    const int tol_hi = __double2hiint(tol);
+    double M[U], E[U], s[U], c[U], d[U];
+    int last[U];  // last Newton step in which the lane was active
+    bool big = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        M[u] = rvl::mean_anomaly(nmot, t[u], epoch, M0);
+        big = big || !(abs_hi(M[u]) < kHiTrigMax);
+        last[u] = 1;
+    }
+    bool fallback = __any_sync(kFull, big || !(ec >= -0.99)) || !(tol_hi < rvl::kHiFinal) || itmax < 2;
+    int trip = 1;
+    if (!fallback) {
+        // pass 1 + step 1: E0 = M, every lane active (trueanomaly.c:19-29)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            rvl::sincos_fast(kt, M[u], s[u], c[u]);
+            double En;
+            rvl::newton_step(M[u], s[u], c[u], M[u], ec, En);
+            d[u] = rvl::sub(En, M[u]);  // exact
+            E[u] = En;
+        }
+#pragma unroll 2
+        for (;;) {
+            float hm = 0.0f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) hm = fmaxf(hm, fabsf(__int_as_float(__double2hiint(d[u]))));
+            const int wmax = (int)__reduce_max_sync(kFull, __float_as_uint(hm));
+            // (1) bring (sin E, cos E) up to date with the step d just taken
+            if (wmax < kHiSmall) {
+                if (wmax < tol_hi) {  // every |d| < tol: the last pass
+#pragma unroll
+                    for (int u = 0; u < U; ++u) rvl::advance_final(kt, d[u], s[u], c[u]);
+                    break;
+                }
+                if (wmax < kHiTiny) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) rvl::advance_tiny(kt, d[u], s[u], c[u]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) rvl::advance_small(kt, d[u], s[u], c[u]);
+                }
+            } else if (wmax < kHiMedium) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) rvl::advance_medium(kt, d[u], s[u], c[u]);
+            } else {
+                // |E| can only leave the fast range after >= 3 Newton steps (|step| <= 100 |f|)
+                if (trip > 2 && any_big<U>(E)) { fallback = true; break; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) rvl::sincos_fast(kt, E[u], s[u], c[u]);
+            }
+            if (trip >= itmax) break;  // the cap (trueanomaly.c:32-33)
+            ++trip;
+            // (2) one Newton step (trueanomaly.c:25-29); frozen lanes (|d| <= tol, :21) get r = 0
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool pa = fabs(d[u]) > tol;
+                const double x = rvl::fma_(-ec, c[u], 1.0);
+                const double y0 = rvl::rcp_seed(x);
+                const double y = __hiloint2double(pa ? __double2hiint(y0) : 0, 0);
+                const double e = rvl::fma_(-x, y, 1.0);
+                const double r = rvl::fma_(y, rvl::fma_(e, e, e), y);
+#if RVL_FMA_F
+                const double f = rvl::sub(rvl::fma_(-ec, s[u], E[u]), M[u]);
+#else
+                const double f = rvl::sub(rvl::sub(E[u], rvl::mul(ec, s[u])), M[u]);
+#endif
+                const double En = rvl::fma_(-f, r, E[u]);
+                d[u] = rvl::sub(En, E[u]);  // exact; 0 for a frozen lane
+                E[u] = En;
+                last[u] = pa ? trip : last[u];  // (one select with a uniform operand)
+            }
+        }
+    }
+    if (fallback) {  // (warp-uniform) restart in the general loop: same arithmetic, same trajectory
+        solve_planet_ref<0, U>(kt, t, pc, tol, itmax, rv, iters, caps);
+        return;
+    }
+    const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
+    const double mAec = lds_f64(pc + 56);
+    if (trip >= itmax) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) caps += (fabs(d[u]) > tol) ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        iters[u] += last[u] - 1;
+        rv[u] = rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec);
     }
 }
 
@@ -342,12 +441,13 @@ __device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const doub
 {
     const int K = m.n_planets;
     bool bad = false;
+    const rvl::KTab kt = rvl::load_ktab();
     if (lane < K) {
         const rvl_planet_desc &pl = m.planet[lane];
         double amp = par_of(pl.amp, row);
-        if (pl.amp_is_log) amp = exp(amp);
+        if (pl.amp_is_log) amp = rvl::exp_cr(amp);
         double per = par_of(pl.period, row);
-        if (pl.period_is_log) per = exp(per);
+        if (pl.period_is_log) per = rvl::exp_cr(per);  // THE nearest double (see rvl_math.h)
         const double a = par_of(pl.e1, row), b = par_of(pl.e2, row);
         double ecc, omega;
         if (pl.ecc_mode == RVL_ECC_SECOS_SESIN) {
@@ -367,7 +467,7 @@ __device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const doub
         const double ec = ecc > 0.99 ? 0.99 : ecc;  // trueanomaly.c:11-12
         double sw, cw;
         if (abs_hi(omega) < kHiTrigMax) {
-            rvl::sincos_fast(omega, sw, cw);
+            rvl::sincos_fast(kt, omega, sw, cw);
         } else {
             const double2 r = sincos_slow(omega);
             sw = r.x;
@@ -429,8 +529,8 @@ struct ItemSums {
 #define RVL_ITEM_INLINE __forceinline__
 #endif
 template <int VARIANT, int U>
-__device__ RVL_ITEM_INLINE ItemSums item_epochs(const HotCtx *hc, uint32_t a_wc, int c_lo, int c_hi,
-                                             int lane)
+__device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCtx *hc, uint32_t a_wc,
+                                                int c_lo, int c_hi, int lane)
 {
     const double tol = hc->tol;
     const int K = hc->K, itmax = hc->itmax, drift_hi = hc->drift_hi, nlin = hc->nlin, N = hc->N;
@@ -459,12 +559,12 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const HotCtx *hc, uint32_t a_wc,
             live[u] = have && (e_base + cu * 32) < N;
             t[u] = lds_f64(a_t + off[u]);
             rvsum[u] = 0.0;
-            it_l[u] = 0;
+            it_l[u] = K;  // every solve takes at least one Newton step; solve_planet adds the rest
         }
         int cap_l = 0;
         for (int p = 0; p < K; ++p) {
             double v[U];
-            solve_planet<VARIANT, U>(t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
+            solve_planet<VARIANT, U>(kt, t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
                                      itmax, v, it_l, cap_l);
 #pragma unroll
             for (int u = 0; u < U; ++u) rvsum[u] = (p == 0) ? v[u] : rvl::add(rvsum[u], v[u]);
@@ -631,6 +731,11 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     }
     __syncthreads();
 
+    // the 17 constants of the sin/cos kernels, loaded once and kept (see rvl_math.h: KTab)
+#ifndef RVL_PIN_KTAB
+#define RVL_PIN_KTAB 1
+#endif
+    const rvl::KTab kt = RVL_PIN_KTAB ? rvl::load_ktab_pinned() : rvl::load_ktab();
     unsigned long long tot_iters = 0, tot_caps = 0, tot_invalid = 0;
     if (a.trace && lane == 0) {
         unsigned long long t;
@@ -711,7 +816,7 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
 
         // ---- the item's epochs: Kepler solves + Gaussian terms (out of line, see item_epochs) ----
         ItemSums sums{0.0, 1.0, 0, 0, 0, 1};
-        if (valid) sums = item_epochs<VARIANT, U>(hc, a_wc, c_lo, c_hi, lane);
+        if (valid) sums = item_epochs<VARIANT, U>(kt, hc, a_wc, c_lo, c_hi, lane);
         double chi = sums.chi, prod = sums.prod;
         int esum = sums.esum;
         const int iters = sums.iters, caps = sums.caps;
@@ -1016,12 +1121,13 @@ __global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *n
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int ii = min(i, n - 1);  // whole warps stay converged; extra lanes duplicate the last
+    const rvl::KTab kt = rvl::load_ktab();
     const double ec = ecc > 0.99 ? 0.99 : ecc;
     const double m = __ldg(M + ii);
     double E = m, s, c, d = 1e300;
     const bool slow = __any_sync(kFull, !(abs_hi(m) < kHiTrigMax) || !(ec >= -0.99));
     if (slow) { const double2 r = sincos_slow(E); s = r.x; c = r.y; }
-    else rvl::sincos_fast(E, s, c);
+    else rvl::sincos_fast(kt, E, s, c);
     int trip = 0;
     for (;;) {
         const bool pa = (fabs(d) > tol) && trip < itmax;
@@ -1033,11 +1139,11 @@ __global__ void trueanomaly_kernel(const double *M, int n, double ecc, double *n
         d = rvl::sub(En, E);
         E = En;
         const int h = abs_hi(d);
-        if (__all_sync(kFull, h < kHiTiny)) rvl::advance_tiny(d, s, c);
-        else if (__all_sync(kFull, h < kHiSmall)) rvl::advance_small(d, s, c);
+        if (__all_sync(kFull, h < kHiTiny)) rvl::advance_tiny(kt, d, s, c);
+        else if (__all_sync(kFull, h < kHiSmall)) rvl::advance_small(kt, d, s, c);
         else if (slow || (trip > 2 && __any_sync(kFull, !(abs_hi(E) < kHiTrigMax)))) {
             const double2 r = sincos_slow(E); s = r.x; c = r.y;
-        } else rvl::sincos_fast(E, s, c);
+        } else rvl::sincos_fast(kt, E, s, c);
     }
     const int cap = (fabs(d) > tol) ? 1 : 0;
     if (i < n) {
@@ -1062,7 +1168,7 @@ __global__ void __launch_bounds__(1024) dfma_peak_kernel(double *out, int iters,
 #pragma unroll
             // multiplier from the constant bank (uniform-register operand), addend in a
             // register: the operand form that reached the highest rate in tools/ubench.cu
-            for (int r = 0; r < R; ++r) x[r] = __fma_rn(x[r], RVL_K(23), b);
+            for (int r = 0; r < R; ++r) x[r] = __fma_rn(x[r], rvl::d_ktab[16], b);
         }
     }
     double s = 0.0;

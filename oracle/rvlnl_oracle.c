@@ -30,6 +30,25 @@
  * whole call returns -1 and leaves the remaining nu untouched.
  * `iters` (optional) accumulates the number of Newton steps taken.
  * ---------------------------------------------------------------------------------------- */
+/* The sin / cos of the Newton loop can be swapped at compile time (-D'ORC_SIN(x)=...'): only
+ * oracle/experiments/libm_sensitivity.py does that, to measure how far the REFERENCE moves when
+ * its libm changes.  Default: the C library's, like the reference. */
+#ifdef ORC_PERTURB
+/* a libm that is one ulp off on 1/16 of its results (deterministic in the value) */
+static double orc_perturb(double y)
+{
+    union { double d; unsigned long long u; } w;
+    w.d = y;
+    if (((w.u * 0x9E3779B97F4A7C15ull) >> 60) == 0) w.u ^= 1ull;
+    return w.d;
+}
+#endif
+#ifndef ORC_SIN
+#define ORC_SIN(x) sin(x)
+#endif
+#ifndef ORC_COS
+#define ORC_COS(x) cos(x)
+#endif
 int orc_trueanomaly(const double *M, int n, double ecc, double *nu, int itmax, double tol,
                     long long *iters)
 {
@@ -41,8 +60,8 @@ int orc_trueanomaly(const double *M, int n, double ecc, double *nu, int itmax, d
         int k = 0;
         do {
             prev = cur;
-            const double f = prev - e * sin(prev) - m;
-            const double fp = 1 - e * cos(prev);
+            const double f = prev - e * ORC_SIN(prev) - m;
+            const double fp = 1 - e * ORC_COS(prev);
             cur = prev - f / fp;
             ++k;
             if (k >= itmax) {

@@ -70,19 +70,19 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
             for (int l = 0; l < W; ++l) all_final = all_final && (abs_hi(d[u][l]) < tol_hi);
         if (all_final && tol_hi < rvl::kHiFinal) {  // the last pass: shorter series, then out
             ++st.trips_tiny;
-            for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_final(d[u][l], s[u][l], c[u][l]);
+            for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_final(rvl::h_ktab, d[u][l], s[u][l], c[u][l]);
             break;
         }
-        if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(d[u][l], s[u][l], c[u][l]); }
-        else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(d[u][l], s[u][l], c[u][l]); }
-        else if (!slow && all_medium) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_medium(d[u][l], s[u][l], c[u][l]); }
+        if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
+        else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
+        else if (!slow && all_medium) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_medium(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
         else {
             ++st.trips_full;
             const bool lib = slow || (trip > 2 && any_big);
             for (int u = 0; u < U; ++u)
                 for (int l = 0; l < W; ++l) {
                     if (lib) { s[u][l] = sin(E[u][l]); c[u][l] = cos(E[u][l]); }
-                    else rvl::sincos_fast(E[u][l], s[u][l], c[u][l]);
+                    else rvl::sincos_fast(rvl::h_ktab, E[u][l], s[u][l], c[u][l]);
                 }
         }
         bool pa[2][W], any_left = false;
@@ -118,9 +118,9 @@ bool point_setup(const rvl_model_desc &m, const double *row, double *wc)
     for (int p = 0; p < K; ++p) {
         const rvl_planet_desc &pl = m.planet[p];
         double amp = par_of(pl.amp, row);
-        if (pl.amp_is_log) amp = exp(amp);
+        if (pl.amp_is_log) amp = rvl::exp_cr(amp);
         double per = par_of(pl.period, row);
-        if (pl.period_is_log) per = exp(per);
+        if (pl.period_is_log) per = rvl::exp_cr(per);
         const double a = par_of(pl.e1, row), b = par_of(pl.e2, row);
         double ecc, omega;
         if (pl.ecc_mode == RVL_ECC_SECOS_SESIN) { ecc = a * a + b * b; omega = atan2(b, a); bad = bad || ecc > 1.0; }
@@ -130,7 +130,7 @@ bool point_setup(const rvl_model_desc &m, const double *row, double *wc)
         if (pl.phase_mode == RVL_PHASE_ML0) M0 = M0 - omega;
         const double ec = ecc > 0.99 ? 0.99 : ecc;
         double sw, cw;
-        if (abs_hi(omega) < kHiTrigMax) rvl::sincos_fast(omega, sw, cw);
+        if (abs_hi(omega) < kHiTrigMax) rvl::sincos_fast(rvl::h_ktab, omega, sw, cw);
         else { sw = sin(omega); cw = cos(omega); }
         const double root = sqrt((1.0 - ec) * (1.0 + ec));
         double *pc = wc + p * kPlanetStride;
@@ -294,7 +294,7 @@ extern "C" double emul_sincos_maxerr(const double *x, int n)
     double worst = 0;
     for (int i = 0; i < n; ++i) {
         double s, c;
-        rvl::sincos_fast(x[i], s, c);
+        rvl::sincos_fast(rvl::h_ktab, x[i], s, c);
         const double es = fabs(s - sin(x[i])), ecs = fabs(c - cos(x[i]));
         if (es > worst) worst = es;
         if (ecs > worst) worst = ecs;
@@ -303,3 +303,4 @@ extern "C" double emul_sincos_maxerr(const double *x, int n)
 }
 
 extern "C" double emul_rcp(double x) { return rvl::rcp(x); }
+extern "C" void emul_exp_cr(const double *x, int n, double *y) { for (int i = 0; i < n; ++i) y[i] = rvl::exp_cr(x[i]); }

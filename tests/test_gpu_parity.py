@@ -499,6 +499,13 @@ def test_kernel_timing_is_opt_in(models):
     m.set_option("timing", 0)
 
 
+def _exp_nearest(v):
+    """exp(v) rounded to the nearest double (200-bit mpmath): what a correctly rounded exp returns."""
+    import mpmath
+    with mpmath.workprec(200):
+        return float(mpmath.exp(mpmath.mpf(float(v))))
+
+
 def test_random_model_structures_vs_numpy_oracle():
     """
     40 seeded random model structures -- every combination the name-driven rules allow: per planet
@@ -570,8 +577,19 @@ def test_random_model_structures_vs_numpy_oracle():
         theta = np.stack([rng.uniform(*box[p], B) for p in m.parnames], axis=1)
         want = om.log_likelihood_batch(theta)
         got = m.log_likelihood_batch(theta)
-        log_period = any("logperiod" in p for p in list(free) + list(fixed))
-        # exp(logperiod) is the one ulp-hypersensitive input
-        ok, worst = lnl_close(got, want, abs_tol=5e-8 if log_period else 1e-9)
+        # exp(logperiod) is the one ulp-hypersensitive input.  The device
+        # decodes it with a CORRECTLY ROUNDED exp; the reference uses numpy's, which is not (its
+        # AVX-512 kernel is one ulp off the nearest double for ~5 % of the arguments, glibc's for
+        # 0.1 %: profiles/r2_exp_rounding.txt).  So: every row on which numpy itself returns the
+        # nearest double must meet the 1e-9 bar; the others differ by the reference's own last bit of
+        # P (observed <= 5e-8 in lnL).
+        exact = np.ones(B, dtype=bool)
+        for p in list(free) + list(fixed):
+            if "logperiod" in p:
+                vals = theta[:, m.parnames.index(p)] if p in free else np.full(B, fixed[p])
+                exact &= np.array([np.exp(v) == _exp_nearest(v) for v in vals])
+        ok, worst = lnl_close(got[exact], want[exact], abs_tol=1e-9)
+        assert ok, (trial, sorted(free), sorted(fixed), worst)
+        ok, worst = lnl_close(got, want, abs_tol=5e-8)
         assert ok, (trial, sorted(free), sorted(fixed), worst)
         m.close()

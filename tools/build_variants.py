@@ -5,15 +5,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from evidence_b200 import build
 
 VARIANTS = {
-    # round-1 arithmetic: FP64 |d|>tol compare, two-rounding E - e sin E, kepler_rv, no short last pass
-    "r1": ["RVL_INT_TOL=0", "RVL_KRV2=0", "RVL_FINAL=0", "RVL_FMA_F=0"],
-    "no_int_tol": ["RVL_INT_TOL=0"],
-    "no_final": ["RVL_FINAL=0"],
-    "no_fma_f": ["RVL_FMA_F=0"],
+    "nopin": ["RVL_PIN_KTAB=0"],   # constants re-loaded by the compiler where it likes
+    "no_fma_f": ["RVL_FMA_F=0"],   # two-rounding E - e sin E
 }
 if __name__ == "__main__":
     d = os.path.join(os.path.dirname(build.OUT), "variants")
     os.makedirs(d, exist_ok=True)
+    for f in os.listdir(d):
+        os.remove(os.path.join(d, f))
     for name, defs in VARIANTS.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
