@@ -16,21 +16,34 @@ import numpy as np
 def make_callbacks(model, priordict):
     """(prior, loglike) in PolyChord's convention: prior(cube)->theta, loglike(theta)->(lnL, [])."""
     parnames = model.parnames
-    sorted_groups = {}
-    for i, p in enumerate(parnames):  # sorted (forced-identifiability) priors, :145-160
+    from .priors import LogSortedUniformPrior, SortedUniformPrior
+    # Sorted (forced-identifiability) priors, evidence/polychord/__init__.py:137-160: the reference
+    # collects EVERY parameter whose prior is a SortedUniformPrior into one group (and every
+    # LogSortedUniformPrior into another), whatever object each parameter holds --
+    # prior_constructor builds one object per parameter -- and applies the LAST such object seen to
+    # the whole group, in parnames order.  (isinstance order as in the reference: the log variant
+    # is tested second there, but as a subclass here it must be tested first.)
+    groups = {"log": [None, []], "lin": [None, []]}
+    plain = []
+    for i, p in enumerate(parnames):
         pr = priordict[p]
-        if type(pr).__name__ in ("SortedUniformPrior", "LogSortedUniformPrior"):
-            sorted_groups.setdefault(id(pr), (pr, []))[1].append(i)
-    plain = [i for i in range(len(parnames))
-             if not any(i in g[1] for g in sorted_groups.values())]
+        if isinstance(pr, LogSortedUniformPrior):
+            groups["log"][0] = pr
+            groups["log"][1].append(i)
+        elif isinstance(pr, SortedUniformPrior):
+            groups["lin"][0] = pr
+            groups["lin"][1].append(i)
+        else:
+            plain.append(i)
 
     def prior(hypercube):
         hypercube = np.asarray(hypercube, dtype=np.float64)
         theta = np.ones_like(hypercube)
         for i in plain:
             theta[i] = priordict[parnames[i]].ppf(hypercube[i])
-        for pr, idx in sorted_groups.values():
-            theta[idx] = pr(hypercube[idx])
+        for pr, idx in groups.values():
+            if idx:
+                theta[idx] = pr(hypercube[idx])
         return theta
 
     def loglike(x):

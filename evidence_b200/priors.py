@@ -483,10 +483,12 @@ def prior_constructor(input_dict, customprior_dict=None):
                 continue
             priortype = parlist[2][0]
             pars = parlist[2][1:]
+            if priortype not in distdict:  # the reference's message (evidence/priors.py:500-503)
+                raise PriorError(f"Parameter {objkey}_{parkey}: Unknown type of prior.")
             try:
                 priordict[objkey + "_" + parkey] = make_prior(priortype, *pars)
-            except PriorError:
-                raise PriorError(f"Parameter {objkey}_{parkey}: Unknown type of prior.")
+            except (PriorError, TypeError) as exc:  # bad shape parameters: keep the real cause
+                raise PriorError(f"Parameter {objkey}_{parkey} ({priortype}): {exc}") from exc
     return priordict
 
 

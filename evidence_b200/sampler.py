@@ -24,7 +24,9 @@ points (MultiNest with one ellipsoid / nestle's 'single' bound); candidates are 
 of ``ndraw`` -- the large batches the device path is built for -- and consumed in order.  Efficient
 for unimodal problems only.
 
-ln Z uncertainty follows Skilling's estimate sigma = sqrt(H / nlive).
+ln Z uncertainty: the larger of Skilling's estimate sqrt(H / nlive) and a bootstrap over the run's
+lineages (``lineage_bootstrap``, the estimate UltraNest's ``num_bootstraps`` makes); likelihood
+plateaus (tied values, e.g. the model's -1e30) are retired as a whole (``retire_groups``).
 """
 import numpy as np
 
@@ -175,6 +177,83 @@ def nested_sample_ellipsoid(loglike, transform, ndim, nlive=400, ndraw=4096, dlo
                         logl=dead_logl, nlive=nlive, seed=seed)
 
 
+
+# ------------------------------------------------------------------------------------------
+# evidence bookkeeping shared by the samplers: tie-aware retirement and the lineage bootstrap
+# ------------------------------------------------------------------------------------------
+def retire_groups(l_sorted, n_live):
+    """
+    Shrinkage bookkeeping for retiring the points with (ascending) log-likelihoods ``l_sorted`` from
+    a set of ``n_live`` live points, one after the other.  Returns (dlogx[len], logw_rel[len]): the
+    change of ln X caused by each point and its ln weight relative to ln X at the start.
+
+    Distinct values: the classic E[ln t] = -1/n with n = n_live, n_live - 1, ...  A group of g points
+    with the SAME value (a likelihood plateau -- e.g. the -1e30 the model returns for an invalid
+    Keplerian, evidence/rvmodel/__init__.py:198-203) is retired as a whole: X shrinks by
+    (n - g) / n and every member gets 1/g of that shell (Fowlie, Handley & Su 2020; UltraNest does
+    the same).  Charging each tied point its own 1/n instead over-estimates X whenever the
+    replacements are drawn from L > L_plateau, and with it ln Z (+0.17 for a 70 % plateau).
+    """
+    l_sorted = np.asarray(l_sorted, dtype=np.float64)
+    m = len(l_sorted)
+    dlogx, logw_rel = np.empty(m), np.empty(m)
+    n_cur, logx, i = int(n_live), 0.0, 0
+    while i < m:
+        j = i
+        while j + 1 < m and l_sorted[j + 1] == l_sorted[i]:
+            j += 1
+        g = j - i + 1
+        if g >= n_cur:
+            raise ValueError("every live point has the same log-likelihood: nothing to integrate")
+        step = -1.0 / n_cur if g == 1 else np.log((n_cur - g) / n_cur)
+        shell = logx + np.log1p(-np.exp(step))  # ln (X_before - X_after)
+        logw_rel[i:j + 1] = shell - np.log(g)
+        dlogx[i:j + 1] = step / g
+        logx += step
+        n_cur -= g
+        i = j + 1
+    return dlogx, logw_rel
+
+
+def lineage_bootstrap(birth, death, root, n_roots, rng, num=30):
+    """
+    Scatter of ln Z under resampling of the run's LINEAGES (what UltraNest's ``num_bootstraps``
+    estimates, evidence/ultranest/__init__.py:172): every point of a run descends from one of the
+    initial live points (its root); a bootstrap draws n_roots roots with replacement, keeps the points
+    of the drawn lineages (with multiplicity) and integrates the evidence again with the number of
+    live points that THOSE lineages had at each death.  Unlike Skilling's sqrt(H/n), which only
+    knows the shrinkage noise, this sees lineages dying out -- modes found by few live points -- which
+    is what dominates the run-to-run scatter on multimodal period posteriors.
+    Returns (std of ln Z over the bootstraps, the ln Z values).
+    """
+    birth, death = np.asarray(birth, dtype=np.float64), np.asarray(death, dtype=np.float64)
+    root = np.asarray(root)
+    order = np.argsort(death, kind="stable")
+    birth, death, root = birth[order], death[order], root[order]
+    birth_sorted_idx = np.argsort(birth, kind="stable")
+    out = []
+    for _ in range(int(num)):
+        mult = np.bincount(rng.integers(0, n_roots, n_roots), minlength=n_roots)[root].astype(np.float64)
+        # live count just before death i: points born below L_i minus points that died below L_i
+        born = np.concatenate([[0.0], np.cumsum(mult[birth_sorted_idx])])
+        n_born = born[np.searchsorted(birth[birth_sorted_idx], death, side="left")]
+        dead_before = np.concatenate([[0.0], np.cumsum(mult)])[:-1]
+        n_alive = n_born - dead_before
+        use = (mult > 0) & (n_alive > 0)
+        if use.sum() < 2:
+            continue
+        # each kept point (multiplicity c) compresses ln X by c / n_alive
+        dl = np.where(use, mult / np.maximum(n_alive, 1e-300), 0.0)
+        logx_after = -np.cumsum(dl)
+        logx_before = logx_after + dl
+        with np.errstate(divide="ignore"):
+            logw = np.where(use, logx_before + np.log1p(-np.exp(-np.maximum(dl, 1e-300))), -np.inf)
+        terms = death + logw
+        mx = np.max(terms[np.isfinite(terms)])
+        out.append(mx + np.log(np.sum(np.exp(terms[np.isfinite(terms)] - mx))))
+    out = np.array(out)
+    return (float(np.std(out)) if len(out) > 1 else 0.0), out
+
 # ------------------------------------------------------------------------------------------
 # slice-sampling replacement (default)
 # ------------------------------------------------------------------------------------------
@@ -290,7 +369,7 @@ def _slice_moves(rng, loglike, transform, u, lmin, chol, nsteps, max_expand=16, 
 
 def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, frac_remain=0.01,
                   seed=0, nsteps=None, batch_fraction=0.2, method="slice", max_calls=500_000_000,
-                  verbose=False, fused=None, speculate=None, **kw):
+                  verbose=False, fused=None, speculate=None, num_bootstraps=30, **kw):
     """
     Seeded vectorised nested sampling; see the module docstring.  ``loglike(theta[n, ndim])`` and
     ``transform(u[n, ndim])`` follow UltraNest's ``vectorized=True`` convention.  Returns a
@@ -311,6 +390,9 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
     ncall = nlive
     logz, h_info, logx = -np.inf, 0.0, 0.0
     dead_theta, dead_logl, dead_logw = [], [], []
+    # lineages: the initial live point every point descends from, and the constraint it was born under
+    root_live, birth_live = np.arange(nlive), np.full(nlive, -np.inf)
+    dead_root, dead_birth = [], []
     niter = 0
 
     def absorb(lval, logw):
@@ -324,22 +406,26 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
 
     while True:
         order = np.argsort(l_live, kind="stable")
-        worst = order[:k]
-        n_cur = nlive
-        for j in worst:  # retire the k worst one by one: shrinkage 1/n with n = nlive, nlive-1, ...
-            logx_new = logx - 1.0 / n_cur
-            logw = logx + np.log1p(-np.exp(logx_new - logx))
-            absorb(l_live[j], logw)
+        # the k worst -- and everything tied with the k-th: a plateau is retired as a whole, before
+        # any replacement is drawn from above it (retire_groups)
+        kk = k
+        while kk < nlive - 2 and l_live[order[kk]] == l_live[order[k - 1]]:
+            kk += 1
+        worst = order[:kk]
+        dlogx, logw_rel = retire_groups(l_live[worst], nlive)
+        for i, j in enumerate(worst):
+            absorb(l_live[j], logx + logw_rel[i])
             dead_theta.append(th_live[j].copy())
             dead_logl.append(l_live[j])
-            dead_logw.append(logw)
-            logx = logx_new
-            n_cur -= 1
+            dead_logw.append(logx + logw_rel[i])
+            dead_root.append(root_live[j])
+            dead_birth.append(birth_live[j])
             niter += 1
+        logx += float(np.sum(dlogx))
         lmin = l_live[worst[-1]]
-        keep = order[k:]
+        keep = order[kk:]
         chol = _whitening(u_live[keep])
-        starts = keep[rng.integers(0, len(keep), k)]
+        starts = keep[rng.integers(0, len(keep), kk)]
         u_new, th_new, l_new, nc = _slice_moves(rng, loglike, transform, u_live[starts].copy(),
                                                 lmin, chol, nsteps, fused=fused,
                                                 speculate=speculate)
@@ -348,6 +434,7 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
         l_new = np.where(stuck, l_live[starts], l_new)
         th_new[stuck] = th_live[starts][stuck]
         u_live[worst], th_live[worst], l_live[worst] = u_new, th_new, l_new
+        root_live[worst], birth_live[worst] = root_live[starts], lmin
         if ncall > max_calls:
             raise RuntimeError("nested_sample: max_calls exceeded")
         log_remain = np.max(l_live) + logx
@@ -365,6 +452,8 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
         dead_theta.append(th_live[j].copy())
         dead_logl.append(l_live[j])
         dead_logw.append(logw_live)
+        dead_root.append(root_live[j])
+        dead_birth.append(birth_live[j])
     dead_logl, dead_logw = np.array(dead_logl), np.array(dead_logw)
     logwt = dead_logl + dead_logw - logz
     weights = np.exp(logwt - np.max(logwt))
@@ -373,7 +462,13 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
     nsamp = max(1, int(1.0 / np.sum(weights ** 2)))
     pos = (rng.random() + np.arange(nsamp)) / nsamp
     idx = np.minimum(np.searchsorted(np.cumsum(weights), pos), len(weights) - 1)
-    return NestedResult(logz=float(logz), logzerr=float(np.sqrt(max(h_info, 0.0) / nlive)),
+    skilling = float(np.sqrt(max(h_info, 0.0) / nlive))
+    bs_std, bs = lineage_bootstrap(dead_birth, dead_logl, dead_root, nlive,
+                                   np.random.default_rng([int(seed), 0xB007]), num_bootstraps)
+    # reported uncertainty: the lineage bootstrap (which contains the shrinkage noise) where it is
+    # larger than Skilling's estimate -- on multimodal posteriors it is, several times
+    return NestedResult(logz=float(logz), logzerr=float(max(skilling, bs_std)),
+                        logzerr_skilling=skilling, logzerr_bootstrap=bs_std,
                         ncall=int(ncall), niter=int(niter), information=float(h_info),
                         samples=theta[idx], weighted_samples=theta, weights=weights,
                         logl=dead_logl, nlive=nlive, seed=seed, method="slice")

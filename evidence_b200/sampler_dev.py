@@ -24,7 +24,9 @@ is device-agnostic torch code, which is how the CPU tests drive it with an analy
 """
 import math
 
-from .sampler import NestedResult
+import numpy as np
+
+from .sampler import NestedResult, lineage_bootstrap, retire_groups
 
 
 def _whitening(torch, u):
@@ -125,7 +127,7 @@ def _slice_moves(torch, gen, fused, u, theta, lmin, chol, nsteps, m, max_expand,
 
 def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, seed=0, nsteps=None,
                          batch_fraction=0.2, speculate=None, device="cuda", max_expand=16,
-                         max_shrink=64, max_calls=2_000_000_000, verbose=False):
+                         max_shrink=64, max_calls=2_000_000_000, verbose=False, num_bootstraps=30):
     """
     Nested sampling with every array on ``device``.  ``fused(U[n, ndim]) -> (theta[n, ndim],
     lnL[n])`` maps unit-cube points to parameters and log-likelihoods on that device
@@ -152,20 +154,34 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
     logx = 0.0
     logz = torch.tensor(-math.inf, dtype=f64, device=dev)
     dead_theta, dead_logl, dead_logw = [], [], []
+    # lineages (see sampler.lineage_bootstrap): root live point and birth constraint of every point
+    root_live = torch.arange(nlive, device=dev)
+    birth_live = torch.full((nlive,), -math.inf, dtype=f64, device=dev)
+    dead_root, dead_birth = [], []
     niter = 0
+    l_sorted, order = torch.sort(l_live, stable=True)
+    # points tied with the k-th worst are retired with it (a plateau goes as a whole: retire_groups);
+    # the count rides on the one read-back per round
+    kk = int((l_sorted <= l_sorted[k - 1]).sum())
     while True:
-        l_sorted, order = torch.sort(l_live, stable=True)
-        worst, keep = order[:k], order[k:]
-        logw = logx + logw_rel
-        logz = torch.logaddexp(logz, torch.logsumexp(l_sorted[:k] + logw, 0))
+        kk = min(kk, nlive - 2)
+        worst, keep = order[:kk], order[kk:]
+        if kk == k:
+            logw, dx = logx + logw_rel, round_shrink
+        else:  # a plateau round (rare: invalid-Keplerian sentinels at the start of a run)
+            dlx, lw = retire_groups(l_sorted[:kk].cpu().numpy(), nlive)
+            logw, dx = logx + torch.from_numpy(lw).to(dev), -float(dlx.sum())
+        logz = torch.logaddexp(logz, torch.logsumexp(l_sorted[:kk] + logw, 0))
         dead_theta.append(th_live[worst])
-        dead_logl.append(l_sorted[:k])
+        dead_logl.append(l_sorted[:kk])
         dead_logw.append(logw)
-        logx -= round_shrink
-        niter += k
-        lmin = l_sorted[k - 1]
+        dead_root.append(root_live[worst])
+        dead_birth.append(birth_live[worst])
+        logx -= dx
+        niter += kk
+        lmin = l_sorted[kk - 1]
         chol = _whitening(torch, u_live[keep])
-        starts = keep[torch.randint(0, len(keep), (k,), generator=gen, device=dev)]
+        starts = keep[torch.randint(0, len(keep), (kk,), generator=gen, device=dev)]
         u_new, th_new, l_new, nc = _slice_moves(torch, gen, fused, u_live[starts].clone(),
                                                 th_live[starts].clone(), lmin, chol, nsteps, m,
                                                 max_expand, max_shrink, m_out=m_out)
@@ -173,22 +189,28 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
         stuck = ~torch.isfinite(l_new)  # a walker that never moved is a copy of its start point
         l_new = torch.where(stuck, l_live[starts], l_new)
         u_live[worst], th_live[worst], l_live[worst] = u_new, th_new, l_new
+        root_live[worst] = root_live[starts]
+        birth_live[worst] = lmin
         if ncall > max_calls:
             raise RuntimeError("nested_sample_device: max_calls exceeded")
         # UltraNest's two criteria (evidence/ultranest/__init__.py:181-185); one read-back per round
-        log_remain = l_live.max() + logx
+        l_sorted, order = torch.sort(l_live, stable=True)
+        log_remain = l_sorted[-1] + logx
         total = torch.logaddexp(logz, log_remain)
-        lr, tt, lz = (float(x) for x in torch.stack([log_remain, total, logz]).cpu())
+        tied = (l_sorted <= l_sorted[k - 1]).sum().to(f64)
+        lr, tt, lz, kk = (float(x) for x in torch.stack([log_remain, total, logz, tied]).cpu())
+        kk = int(kk)
         if verbose and (niter // k) % 20 == 0:
             print(f"it={niter} lnZ={lz:.3f} ln(remain/Z)={lr - lz:.2f} ncall={ncall}")
         if lr - tt < math.log(frac_remain) and tt - lz < dlogz:
             break
-    l_sorted, order = torch.sort(l_live, stable=True)
     logw_live = torch.full((nlive,), logx - math.log(nlive), dtype=f64, device=dev)
     logz = torch.logaddexp(logz, torch.logsumexp(l_sorted + logw_live, 0))
     dead_theta.append(th_live[order])
     dead_logl.append(l_sorted)
     dead_logw.append(logw_live)
+    dead_root.append(root_live[order])
+    dead_birth.append(birth_live[order])
     theta = torch.cat(dead_theta)
     logl = torch.cat(dead_logl)
     logwt = logl + torch.cat(dead_logw) - logz
@@ -200,7 +222,12 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
     pos = (float(torch.rand((), generator=gen, dtype=f64, device=dev)) +
            torch.arange(nsamp, dtype=f64, device=dev)) / nsamp
     idx = torch.clamp(torch.searchsorted(torch.cumsum(weights, 0), pos), max=len(weights) - 1)
-    return NestedResult(logz=float(logz), logzerr=float(math.sqrt(max(h_info, 0.0) / nlive)),
+    skilling = math.sqrt(max(h_info, 0.0) / nlive)
+    bs_std, _ = lineage_bootstrap(torch.cat(dead_birth).cpu().numpy(), logl.cpu().numpy(),
+                                  torch.cat(dead_root).cpu().numpy(), nlive,
+                                  np.random.default_rng([int(seed), 0xB007]), num_bootstraps)
+    return NestedResult(logz=float(logz), logzerr=float(max(skilling, bs_std)),
+                        logzerr_skilling=skilling, logzerr_bootstrap=bs_std,
                         ncall=int(ncall), niter=int(niter), information=h_info,
                         samples=theta[idx].cpu().numpy(), weighted_samples=theta.cpu().numpy(),
                         weights=weights.cpu().numpy(), logl=logl.cpu().numpy(), nlive=nlive,

@@ -36,7 +36,9 @@ except ImportError:
 
 
 class Output:
-    pass
+    """Attribute bag of a run, pickled as such (evidence/ultranest/__init__.py:200-229, 262-297):
+    the reference's post-processing un-pickles it and reads attributes (``output.file_root``,
+    ``output.rundict``, ``output.datadict``, ... -- evidence/post_processing.py:34-89)."""
 
 
 def _torch_device(model):
@@ -121,6 +123,8 @@ def run(model, rundict, priordict, ultrasettings=None):
         res = sampler.results
         logz, logzerr, ncall, samples = res["logz"], res["logzerr"], res["ncall"], res["samples"]
         name = "UltraNest"
+        impl = f"ultranest {getattr(ultranest, '__version__', '?')}, vectorized={settings['vectorized']}, " \
+               f"stepsampler={settings['stepsampler']}"
         if settings["plot"]:
             sampler.plot()
     else:
@@ -145,7 +149,12 @@ def run(model, rundict, priordict, ultrasettings=None):
                                 method=settings["builtin_method"],
                                 seed=0 if settings["seed"] is None else settings["seed"])
         logz, logzerr, ncall, samples = res.logz, res.logzerr, res.ncall, res.samples
-        name = "b200-nested"
+        # the reference's post-processing knows 'PolyChord' and 'UltraNest' only and, for the latter,
+        # reads run1/chains/weighted_post.txt (evidence/post_processing.py:66-88): same label, same
+        # file, and the implementation named beside it
+        name = "UltraNest"
+        impl = f"evidence_b200.sampler ({settings['builtin_method']}); ultranest not used"
+        write_weighted_post(settings["log_dir"], parnames, res)
     tf = time.process_time()
     t_wall = time.perf_counter() - t_wall
     if size > 1:
@@ -159,7 +168,7 @@ def run(model, rundict, priordict, ultrasettings=None):
         output.runtime = datetime.timedelta(seconds=tf - ti)
         output.walltime = t_wall
         output.rundict = rundict.copy()
-        output.datadict = dict(getattr(model, "datadict", {}))
+        output.datadict = dict(getattr(model, "datadict", {}))  # host tables (frames / arrays) only
         output.fixedpardict = dict(getattr(model, "fixedpardict", {}))
         model_path = getattr(model, "model_path", None)
         output.model_name = str(Path(model_path).stem) if model_path else type(model).__name__
@@ -170,6 +179,7 @@ def run(model, rundict, priordict, ultrasettings=None):
         output.parnames = parnames
         output.ndim = ndim
         output.sampler = name
+        output.sampler_impl = impl
         output.base_dir = settings["log_dir"]
         output.file_root = settings["file_root"]
         output.logZ = float(logz)
@@ -191,14 +201,28 @@ def run(model, rundict, priordict, ultrasettings=None):
     return output
 
 
+def write_weighted_post(log_dir, parnames, res):
+    """``<log_dir>/run1/chains/weighted_post.txt`` in UltraNest's layout (``weight logl <params>``,
+    space separated), which the reference's post-processing reads for the log-likelihoods and
+    weights of the posterior (evidence/post_processing.py:85-88)."""
+    pts, w, logl = res.get("weighted_samples"), res.get("weights"), res.get("logl")
+    if pts is None or w is None or logl is None:
+        return None
+    chains = os.path.join(log_dir, "run1", "chains")
+    os.makedirs(chains, exist_ok=True)
+    path = os.path.join(chains, "weighted_post.txt")
+    np.savetxt(path, np.column_stack([np.asarray(w), np.asarray(logl), np.asarray(pts)]),
+               header=" ".join(["weight", "logl"] + list(parnames)), comments="")
+    return path
+
+
 def dump2pickle(output, filename, savedir=None):
-    """Pickle ``output`` next to the run directory, evidence/ultranest/__init__.py:262-297."""
-    out = dict(output.__dict__)
-    out.pop("datadict", None)  # data frames may hold device-side handles' inputs; keep it light
+    """Pickle the ``Output`` OBJECT next to the run directory, like
+    evidence/ultranest/__init__.py:262-297 (``datadict`` included: post-processing reads it)."""
     pickledir = Path(output.base_dir).parent if savedir is None else savedir
     os.makedirs(pickledir, exist_ok=True)
     with open(os.path.join(pickledir, filename), "wb") as f:
-        pickle.dump(out, f)
+        pickle.dump(output, f)
 
 
 def set_ultrasettings(rundict, ultrasettings, ndim, nderived, isodate, parnames):

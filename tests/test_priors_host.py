@@ -47,3 +47,49 @@ def test_device_descriptors_pack_tables():
     assert descs[2].p[1] == 1.0 and descs[1].p[1] == 0.0
     cdf = tables[descs[2].table_offset: descs[2].table_offset + descs[2].table_len]
     assert np.all(np.diff(cdf) > 0)
+
+
+def test_prior_constructor_reports_the_real_cause():
+    # an unknown name keeps the reference's message (evidence/priors.py:500-503) ...
+    with pytest.raises(priors.PriorError, match="Unknown type of prior"):
+        priors.prior_constructor({"a": {"b": [0, 1, ["Nope", 1]]}})
+    # ... a known prior with bad shape parameters says what is wrong with them
+    with pytest.raises(priors.PriorError, match="a_b .Uniform.: Uniform needs xmin < xmax"):
+        priors.prior_constructor({"a": {"b": [0, 1, ["Uniform", 3, 1]]}})
+
+
+def test_polychord_sorted_priors_form_one_group():
+    """evidence/polychord/__init__.py:137-160: all parameters with a SortedUniform prior are
+    transformed together (prior_constructor builds one prior object PER parameter), so the periods
+    come out non-decreasing whatever the cube says."""
+    from evidence_b200 import polychord
+
+    class FakeModel:
+        parnames = sorted(["planet1_period", "planet2_period", "planet3_period", "planet1_k1",
+                           "planet2_logk", "planet3_logk"])
+
+        def log_likelihood(self, x):
+            return -1.0
+
+    input_dict = {f"planet{k}": {"period": [0.0, 1, ["SortedUniform", 1.0, 100.0]]} for k in (1, 2, 3)}
+    input_dict["planet1"]["k1"] = [0.0, 1, ["Uniform", 0.0, 10.0]]
+    input_dict["planet2"]["logk"] = [0.0, 1, ["SortedLogUniform", 0.1, 10.0]]
+    input_dict["planet3"]["logk"] = [0.0, 1, ["SortedLogUniform", 0.1, 10.0]]
+    priordict = priors.prior_constructor(input_dict)
+    assert len({id(priordict[f"planet{k}_period"]) for k in (1, 2, 3)}) == 3  # separate objects
+    prior, loglike = polychord.make_callbacks(FakeModel(), priordict)
+    names = FakeModel.parnames
+    rng = np.random.default_rng(0)
+    for cube in [np.array([0.5, 0.9, 0.3, 0.1, 0.7, 0.2])] + list(rng.random((20, 6))):
+        theta = prior(cube)
+        per = [theta[names.index(f"planet{k}_period")] for k in (1, 2, 3)]
+        logk = [theta[names.index(f"planet{k}_logk")] for k in (2, 3)]
+        assert per[0] <= per[1] <= per[2] and 1.0 <= per[0] and per[2] <= 100.0
+        assert logk[0] <= logk[1] and 0.1 <= logk[0] and logk[1] <= 10.0
+        assert theta[names.index("planet1_k1")] == pytest.approx(10.0 * cube[names.index("planet1_k1")])
+    # the reference applies forced identifiability to the group in parnames order
+    cube = np.array([0.5, 0.9, 0.3, 0.1, 0.7, 0.2])
+    idx = [names.index(f"planet{k}_period") for k in (1, 2, 3)]
+    want = 1.0 + 99.0 * priors.forced_identifiability_transform(cube[idx])
+    assert np.allclose(prior(cube)[idx], want)
+    assert loglike(prior(cube)) == (-1.0, [])

@@ -60,7 +60,78 @@ def test_runner_output_contract(tmp_path):
     assert out.file_root.startswith("gaussian_2d_k0_nlive100_ncores1_ultranest_")
     assert list(out.samples.columns) == model.parnames
     pkl = os.path.join(os.path.dirname(out.base_dir), out.file_root + ".pkl")
-    assert pickle.load(open(pkl, "rb"))["logZ"] == out.logZ
+    back = pickle.load(open(pkl, "rb"))  # the OBJECT, as the reference pickles it (:262-297)
+    assert back.logZ == out.logZ and back.file_root == out.file_root and back.rundict == out.rundict
+    assert hasattr(back, "datadict") and back.sampler == "UltraNest" and "evidence_b200.sampler" in back.sampler_impl
+    # what the reference's post-processing reads for an UltraNest run (post_processing.py:85-88)
+    import pandas as pd
+    wp = pd.read_csv(os.path.join(out.base_dir, "run1/chains/weighted_post.txt"), sep=" ")
+    assert list(wp.columns) == ["weight", "logl"] + model.parnames
+    assert abs(wp["weight"].sum() - 1.0) < 1e-9 and np.all(np.diff(wp["logl"]) >= 0)
+
+
+@pytest.fixture
+def ultranest_double(monkeypatch):
+    """The test double of the absent third-party package (tests/doubles/ultranest)."""
+    import sys
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(os.path.abspath(__file__)), "doubles"))
+    for name in [m for m in sys.modules if m == "ultranest" or m.startswith("ultranest.")]:
+        monkeypatch.delitem(sys.modules, name)
+    import ultranest
+    assert ultranest.__version__.endswith("test-double")
+    yield ultranest
+    for name in [m for m in sys.modules if m == "ultranest" or m.startswith("ultranest.")]:
+        sys.modules.pop(name, None)
+
+
+@pytest.mark.parametrize("stepsampler,want_sizes", [("none", "region"), ("population-slice", "pop"),
+                                                    ("region-slice", "one")])
+def test_runner_ultranest_branch_through_the_double(tmp_path, ultranest_double, stepsampler, want_sizes):
+    """The `which == "ultranest"` branch (evidence/ultranest/__init__.py:165-185 with the
+    `vectorized` switch of :171 turned on): constructor keywords, step-sampler choice, run call,
+    results, pickle and weighted_post, against UltraNest's calling convention."""
+    seen = {}
+    real_ctor = ultranest_double.ReactiveNestedSampler
+
+    class Spy(real_ctor):
+        def __init__(self, *a, **kw):
+            seen["kw"] = kw
+            seen["names"] = a[0]
+            super().__init__(*a, **kw)
+            seen["sampler"] = self
+    ultranest_double.ReactiveNestedSampler = Spy
+    model = GaussianModel(2)
+    priordict = {p: priors.Uniform(-10, 10) for p in model.parnames}
+    rundict = {"target": "gauss", "runid": "un", "save_dir": str(tmp_path), "nplanets": 0}
+    out = runner.run(model, rundict, priordict, {"nlive": 100, "sampler": "auto", "nsteps": 4,
+                                                 "ndraw_min": 64, "ndraw_max": 256,
+                                                 "stepsampler": stepsampler})
+    kw = seen["kw"]
+    assert kw["vectorized"] is True and kw["ndraw_min"] == 64 and kw["ndraw_max"] == 256
+    assert kw["num_test_samples"] == 100 and kw["num_bootstraps"] == 30  # :165-172
+    assert list(kw["wrapped_params"]) == [False, False] and seen["names"] == model.parnames
+    assert kw["log_dir"].endswith("ultraresults")
+    sizes = np.array(seen["sampler"].call_sizes)
+    if want_sizes == "region":     # region sampling: ndraw_min .. ndraw_max candidates per call
+        assert sizes[0] == 100 and 1 <= sizes[1:].min() and sizes[1:].max() <= 256 and np.median(sizes[1:]) > 20
+    elif want_sizes == "pop":      # population step sampler: up to popsize = ndraw_min walkers per call
+        assert sizes[0] == 100 and sizes[1:].max() == 64 and sizes[1:].mean() > 8
+    else:                          # the reference's RegionSliceSampler: one point per call
+        assert sizes[0] == 100 and sizes[1:].max() == 1
+    assert abs(out.logZ + 4.1536) < 0.5 and out.sampler == "UltraNest" and "test-double" in out.sampler_impl
+    assert out.nlike == int(sizes.sum())
+    back = pickle.load(open(os.path.join(os.path.dirname(out.base_dir), out.file_root + ".pkl"), "rb"))
+    assert back.logZ == out.logZ
+    assert os.path.exists(os.path.join(out.base_dir, "run1/chains/weighted_post.txt"))
+
+
+def test_ultranest_double_rejects_wrong_shapes(ultranest_double):
+    with pytest.raises(ValueError, match="loglikelihood"):
+        ultranest_double.ReactiveNestedSampler(["a", "b"], lambda th: np.zeros((len(th), 1)),
+                                               lambda u: u, vectorized=True)
+    with pytest.raises(ValueError, match="transform"):
+        ultranest_double.ReactiveNestedSampler(["a", "b"], lambda th: np.zeros(len(th)),
+                                               lambda u: u[:, :1], vectorized=True)
 
 
 def test_settings_defaults_match_the_reference():
@@ -149,3 +220,30 @@ def test_device_resident_sampler_on_cpu_tensors():
     # the look-ahead depth does not change the distribution (here: not even the chain)
     c = nested_sample_device(fused, ndim, nlive=120, seed=5, nsteps=6, device="cpu", speculate=2)
     assert abs(c.logz - a.logz) < 3 * (a.logzerr + c.logzerr)
+
+
+def test_likelihood_plateau_is_retired_as_a_whole():
+    """70 % of the prior returns the model's invalid-Keplerian sentinel (-1e30,
+    evidence/rvmodel/__init__.py:198-203): the tied points are retired together with X *= (n-g)/n
+    (Fowlie et al. 2020) -- charging each its own 1/n biases ln Z by +0.17 here."""
+    from evidence_b200.sampler import retire_groups
+    a = 10.0 * np.sqrt(0.3)  # valid region: the central square holding 30 % of the prior volume
+
+    def loglike(th):
+        out = -0.5 * np.sum(th ** 2, axis=1)
+        out[np.any(np.abs(th) > a, axis=1)] = -1e30
+        return out
+    want = np.log(2 * np.pi / 400.0)  # the Gaussian sits well inside the valid region
+    errs, sig = [], []
+    for seed in range(6):
+        r = nested_sample(loglike, lambda u: -10 + 20 * u, 2, nlive=400, seed=seed, nsteps=8)
+        errs.append(r.logz - want)
+        sig.append(r.logzerr)
+    assert abs(np.mean(errs)) < 0.08, (errs, sig)          # (the per-point 1/n rule gives +0.17)
+    assert np.std(errs) < 2.5 * np.mean(sig) + 0.05
+    # the bookkeeping itself: a plateau of g out of n points shrinks X by (n - g) / n
+    dlogx, logw = retire_groups(np.array([-1e30] * 7 + [-3.0, -2.0]), 10)
+    assert np.isclose(dlogx[:7].sum(), np.log(3 / 10)) and np.allclose(logw[:7], np.log(0.7 / 7))
+    assert np.isclose(dlogx[7], -1 / 3) and np.isclose(dlogx[8], -1 / 2)
+    with pytest.raises(ValueError):
+        retire_groups(np.array([-1.0, -1.0]), 2)
