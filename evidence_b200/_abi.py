@@ -58,6 +58,14 @@ class rvl_counters_t(Structure):
                 ("n_invalid", c_uint64)]
 
 
+class rvl_slice_args(Structure):
+    _fields_ = ([("k", c_int32), ("d", c_int32), ("n_out", c_int32), ("m", c_int32),
+                 ("seed", c_uint64), ("move", ctypes.c_uint32), ("shrink_round", ctypes.c_uint32)] +
+                [(n, c_uint64) for n in ("lmin", "chol", "u", "theta", "lcur", "dirn", "lo", "hi", "lo2",
+                                         "hi2", "tval", "pending", "cand_out", "inside_out", "ll_out",
+                                         "cand", "inside", "cand_ll", "cand_th", "stats")])
+
+
 _dp = POINTER(c_double)
 
 # name -> (restype, argtypes); every symbol include/rvlnl.h declares
@@ -105,6 +113,8 @@ SYMBOLS = {
     "rvl_order_planets": (c_int32, [c_int32, _dp, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32),
                                     c_int32, c_int32, _dp, _dp]),
     "rvl_order_last_error": (c_char_p, []),
+    "rvl_slice_phase": (c_int32, [c_int32, POINTER(rvl_slice_args), c_void_p]),
+    "rvl_slice_last_error": (c_char_p, []),
     "rvl_plan_describe": (c_int32, [POINTER(c_int32), c_int64, POINTER(c_int64), c_int32]),
 }
 

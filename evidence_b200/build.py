@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "rvlnl.cu")
 SRC_FIP = os.path.join(_HERE, "csrc", "rvfip.cu")
 SRC_ORDER = os.path.join(_HERE, "csrc", "rvorder.cu")
-DEPS = [SRC, SRC_FIP, SRC_ORDER, os.path.join(_HERE, "csrc", "rvl_math.h"),
+SRC_SLICE = os.path.join(_HERE, "csrc", "rvslice.cu")
+DEPS = [SRC, SRC_FIP, SRC_ORDER, SRC_SLICE, os.path.join(_HERE, "csrc", "rvl_math.h"),
         os.path.join(os.path.dirname(_HERE), "include", "rvlnl.h")]
 OUT = os.path.join(_HERE, "librvlnl.so")
 
@@ -42,14 +43,14 @@ def needs_build():
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """Compile evidence_b200/csrc/{rvlnl,rvfip,rvorder}.cu -> evidence_b200/librvlnl.so for sm_100a.
+    """Compile evidence_b200/csrc/{rvlnl,rvfip,rvorder,rvslice}.cu -> evidence_b200/librvlnl.so for sm_100a.
     ``defines`` / ``out``: an experimental build beside it (``-DNAME=VALUE`` switches of the kernel
     source, loaded through the RVL_LIB environment variable by the measurement tools)."""
     if out is None and not force and not needs_build():
         return OUT
     out = out or OUT
     cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
-           [f"-D{d}" for d in defines] + ["-o", out, SRC, SRC_FIP, SRC_ORDER])
+           [f"-D{d}" for d in defines] + ["-o", out, SRC, SRC_FIP, SRC_ORDER, SRC_SLICE])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

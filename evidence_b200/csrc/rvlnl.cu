@@ -1233,7 +1233,7 @@ struct rvl_handle {
     unsigned int *d_work = nullptr;            // sm_count + 1 (queues, finished-block counter)
 
     // options
-    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 0, opt_zero_copy = 1, opt_ilp = 2, opt_min_chunks = 8, opt_items_per_warp = 4;
+    int opt_variant = 0, opt_slices = 0, opt_warps = 0, opt_timing = 0, opt_zero_copy = 1, opt_ilp = 0, opt_min_chunks = 8, opt_items_per_warp = 4;
     int opt_sched = 1;          // 1: graded phases (coarse -> fine items), 0: one uniform slice count
     int opt_phase_items = 200;  // items per split phase, in percent of the warps serving a queue
     int opt_max_split = 8;      // finest cut: sub-slices per point and resident range
@@ -1482,7 +1482,13 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     in.ncol = h->ncol;
     in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1) & ~1;
     in.wblock = in.wstride + ((m.ndim + 1) & ~1);
-    in.U = h->opt_variant == 0 ? h->opt_ilp : 1;
+    // epochs per lane in flight: 4 (512 threads, 128 registers) when every warp has a long queue of
+    // whole points -- the per-pass control instructions are then shared by four solves; 2 (896
+    // threads, 72 registers) for sampler-sized batches, where the drain matters more (measured, B200:
+    // config 3 at 131072 theta 24.76 vs 25.08 ms; config 2 at 4096 theta 0.137 vs 0.153 ms)
+    int ilp = h->opt_ilp;
+    if (ilp == 0) ilp = (B >= (long long)h->sm_count * 16 * 16) ? 4 : 2;
+    in.U = h->opt_variant == 0 ? ilp : 1;
     const int w_default = in.U == 1 ? 32 : in.U == 2 ? 28 : in.U == 3 ? 20 : 16;
     const int w_max = in.U <= 2 ? 32 : in.U == 3 ? 20 : 16;
     in.W = std::max(1, std::min(w_max, h->opt_warps > 0 ? h->opt_warps : w_default));
@@ -2129,7 +2135,7 @@ int rvl_set_option(rvl_t *h, const char *name, int64_t value)
     else if (n == "trace") h->opt_trace = value != 0;
     else if (n == "setup_items") h->opt_setup_items = value != 0;
     else if (n == "gather_timeout_ms") h->opt_gather_timeout_ms = std::max<int64_t>(1, value);
-    else if (n == "ilp") { if (value < 1 || value > 4) return fail(h, RVL_EINVAL, "ilp in {1,2,3,4}"); h->opt_ilp = (int)value; }
+    else if (n == "ilp") { if (value < 0 || value > 4) return fail(h, RVL_EINVAL, "ilp in {0 (automatic),1,2,3,4}"); h->opt_ilp = (int)value; }
     else return fail(h, RVL_EINVAL, "unknown option " + n);
     return RVL_OK;
 }

@@ -125,19 +125,100 @@ def _slice_moves(torch, gen, fused, u, theta, lmin, chol, nsteps, m, max_expand,
     return u, theta, lcur, ncall
 
 
+class _NativeSlice:
+    """
+    The slice moves of a round through the hand-written kernels of csrc/rvslice.cu
+    (``rvl_slice_phase``): per move 3-4 bookkeeping launches around 2-3 likelihood launches, nothing
+    read back.  Stepping out evaluates all ``n_out`` positions of both sides at once; shrinkage runs
+    ``rounds`` launches of ``m`` speculated candidates per walker (a walker whose bracket is not
+    resolved after rounds * m candidates keeps its position -- counted in ``unresolved``; with the
+    defaults that is < 1e-3 of the moves).
+    """
+
+    def __init__(self, torch, k, d, dev, seed, n_out=8, m=8, rounds=2):
+        import ctypes
+        from . import _abi
+        self.torch, self.k, self.d, self.n_out, self.m, self.rounds = torch, k, d, n_out, m, rounds
+        self.lib = _abi.load()
+        f64 = torch.float64
+        z = lambda *shape, dt=f64: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        self.dirn, self.lo, self.hi, self.lo2, self.hi2 = z(k, d), z(k), z(k), z(k), z(k)
+        self.tval, self.pending = z(k, m), z(k, dt=torch.int32)
+        self.cand_o, self.inside_o = z(k * 2 * n_out, d), z(k * 2 * n_out, dt=torch.uint8)
+        self.th_o, self.ll_o = z(k * 2 * n_out, d), z(k * 2 * n_out)
+        self.cand, self.inside = z(k * m, d), z(k * m, dt=torch.uint8)
+        self.th, self.ll = z(k * m, d), z(k * m)
+        self.stats = z(2, dt=torch.int64)
+        self.args = _abi.rvl_slice_args()
+        self.args.k, self.args.d, self.args.n_out, self.args.m = k, d, n_out, m
+        self.args.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        for name, t in (("dirn", self.dirn), ("lo", self.lo), ("hi", self.hi), ("lo2", self.lo2),
+                        ("hi2", self.hi2), ("tval", self.tval), ("pending", self.pending),
+                        ("cand_out", self.cand_o), ("inside_out", self.inside_o), ("ll_out", self.ll_o),
+                        ("cand", self.cand), ("inside", self.inside), ("cand_ll", self.ll),
+                        ("cand_th", self.th), ("stats", self.stats)):
+            setattr(self.args, name, t.data_ptr())
+        self._byref = ctypes.byref(self.args)
+        self.move = 0
+
+    def _phase(self, ph):
+        stream = self.torch.cuda.current_stream().cuda_stream
+        rc = self.lib.rvl_slice_phase(ph, self._byref, stream)
+        if rc != 0:
+            raise RuntimeError("rvl_slice_phase: " + self.lib.rvl_slice_last_error().decode())
+
+    @staticmethod
+    def _eval(fused, pts, th_out, ll_out):
+        try:  # a device callable that writes in place (RVModel.transform_loglike_device)
+            fused(pts, theta=th_out, lnl=ll_out)
+        except TypeError:
+            th, ll = fused(pts)
+            th_out.copy_(th)
+            ll_out.copy_(ll)
+
+    def moves(self, fused, u, theta, lcur, lmin, chol, nsteps):
+        """nsteps slice moves of the k walkers u (updated in place with theta and lcur)."""
+        a = self.args
+        chol = chol.contiguous()
+        a.lmin, a.chol = lmin.data_ptr(), chol.data_ptr()
+        a.u, a.theta, a.lcur = u.data_ptr(), theta.data_ptr(), lcur.data_ptr()
+        ncall = 0
+        for _ in range(nsteps):
+            a.move, a.shrink_round = self.move & 0xFFFFFFFF, 0
+            self.move += 1
+            self._phase(0)
+            self._eval(fused, self.cand_o, self.th_o, self.ll_o)
+            self._phase(1)
+            for r in range(self.rounds):
+                self._eval(fused, self.cand, self.th, self.ll)
+                a.shrink_round = r + 1
+                self._phase(2 if r + 1 < self.rounds else 3)
+            ncall += self.k * (2 * self.n_out + self.rounds * self.m)
+        return ncall
+
+
 def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, seed=0, nsteps=None,
                          batch_fraction=0.2, speculate=None, device="cuda", max_expand=16,
-                         max_shrink=64, max_calls=2_000_000_000, verbose=False, num_bootstraps=30):
+                         max_shrink=64, max_calls=2_000_000_000, verbose=False, num_bootstraps=30,
+                         native=None, native_m=8, native_rounds=2, native_out=8):
     """
     Nested sampling with every array on ``device``.  ``fused(U[n, ndim]) -> (theta[n, ndim],
     lnL[n])`` maps unit-cube points to parameters and log-likelihoods on that device
     (``RVModel.transform_loglike_device``).  Returns the same ``NestedResult`` as
     ``sampler.nested_sample`` (arrays as numpy).
+
+    ``native`` (default: on a CUDA device): the slice moves run through the hand-written bookkeeping
+    kernels of csrc/rvslice.cu (``_NativeSlice``) instead of ~150 small torch launches per move;
+    ``native_out`` stepping-out positions per side, ``native_rounds`` x ``native_m`` shrinkage
+    candidates per walker and move, all speculated.  The torch formulation below it is the same
+    sampler for CPU tensors (tests) and the statistical cross-check of the kernels.
     """
     import torch
     dev = torch.device(device)
     f64 = torch.float64
     gen = torch.Generator(device=dev).manual_seed(int(seed))
+    if native is None:
+        native = dev.type == "cuda"
     nsteps = nsteps or max(4, 2 * ndim)
     k = max(1, min(int(batch_fraction * nlive), nlive - 2))
     m = max(1, min(6, 512 // k)) if speculate is None else max(1, int(speculate))
@@ -159,6 +240,7 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
     birth_live = torch.full((nlive,), -math.inf, dtype=f64, device=dev)
     dead_root, dead_birth = [], []
     niter = 0
+    natives, move_no = {}, 0
     l_sorted, order = torch.sort(l_live, stable=True)
     # points tied with the k-th worst are retired with it (a plateau goes as a whole: retire_groups);
     # the count rides on the one read-back per round
@@ -182,9 +264,19 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
         lmin = l_sorted[kk - 1]
         chol = _whitening(torch, u_live[keep])
         starts = keep[torch.randint(0, len(keep), (kk,), generator=gen, device=dev)]
-        u_new, th_new, l_new, nc = _slice_moves(torch, gen, fused, u_live[starts].clone(),
-                                                th_live[starts].clone(), lmin, chol, nsteps, m,
-                                                max_expand, max_shrink, m_out=m_out)
+        if native:
+            if kk not in natives:
+                natives[kk] = _NativeSlice(torch, kk, ndim, dev, seed, n_out=native_out, m=native_m,
+                                           rounds=native_rounds)
+            natives[kk].move = move_no
+            u_new, th_new = u_live[starts].clone(), th_live[starts].clone()
+            l_new = torch.full((kk,), float("nan"), dtype=f64, device=dev)
+            nc = natives[kk].moves(fused, u_new, th_new, l_new, lmin.reshape(1).clone(), chol, nsteps)
+            move_no += nsteps
+        else:
+            u_new, th_new, l_new, nc = _slice_moves(torch, gen, fused, u_live[starts].clone(),
+                                                    th_live[starts].clone(), lmin, chol, nsteps, m,
+                                                    max_expand, max_shrink, m_out=m_out)
         ncall += nc
         stuck = ~torch.isfinite(l_new)  # a walker that never moved is a copy of its start point
         l_new = torch.where(stuck, l_live[starts], l_new)
@@ -231,4 +323,6 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
                         ncall=int(ncall), niter=int(niter), information=h_info,
                         samples=theta[idx].cpu().numpy(), weighted_samples=theta.cpu().numpy(),
                         weights=weights.cpu().numpy(), logl=logl.cpu().numpy(), nlive=nlive,
-                        seed=seed, method="slice-device")
+                        seed=seed, method="slice-device" + ("-native" if native else ""),
+                        unresolved_moves=int(sum(int(n.stats[0]) for n in natives.values())),
+                        accepted_moves=int(sum(int(n.stats[1]) for n in natives.values())))

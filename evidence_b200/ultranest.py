@@ -137,7 +137,7 @@ def run(model, rundict, priordict, ultrasettings=None):
             from .sampler_dev import nested_sample_device
             if not hasattr(model, "transform_loglike_device"):
                 raise ValueError("'builtin_method': 'slice-device' needs the device model")
-            res = nested_sample_device(lambda U: model.transform_loglike_device(U), ndim,
+            res = nested_sample_device(model.transform_loglike_device, ndim,
                                        nlive=settings["nlive"], dlogz=settings["dlogz"],
                                        frac_remain=settings["frac_remain"], nsteps=settings["nsteps"],
                                        seed=0 if settings["seed"] is None else settings["seed"],

@@ -5,7 +5,12 @@ independent run per GPU -- replicas, no collective.
     python examples/evidence_ladder.py --kmax 3                      # one GPU, the k's in sequence
     torchrun --nproc-per-node 6 examples/evidence_ladder.py --kmax 5 # rank r takes k = r, r+6, ...
 
-Each line of output is one JSON record {k, logz, logzerr, ncall, seconds, device}.  On one GPU the
+    ... --cpu-kmax 2   # also run the SAME seeded sampler on the CPU checker for k <= 2
+
+Each line of output is one JSON record {k, logz, logzerr, ncall, seconds, device} (+ cpu_logz,
+cpu_logzerr, cpu_seconds with --cpu-kmax: the C restatement of the reference path,
+oracle/rvlnl_oracle.c, on the host cores -- test infrastructure, used here as the CPU reference
+ln Z that BASELINE.json's configs[3] asks to be printed beside the device's).  On one GPU the
 ladder ends with what the reference's fip_criterion.py does with such runs: p(k|y) from the
 evidences and the FIP periodogram of the posterior periods, accumulated on the device
 (evidence_b200.fip), and prints the periods where the false inclusion probability is lowest.
@@ -24,6 +29,29 @@ from evidence_b200 import fip, priors, synth  # noqa: E402
 from evidence_b200.rvmodel import RVModel  # noqa: E402
 from evidence_b200.sampler import nested_sample  # noqa: E402
 
+_CPU = {}
+
+
+def _cpu_block(args):
+    """One block of rows through the C restatement of the reference path (worker process)."""
+    from oracle import rv_oracle
+    desc, t, v, s, ids, n_inst, block = args
+    return rv_oracle.c_loglike_batch(desc, t, v, s, ids, n_inst, block)[0]
+
+
+def cpu_loglike_factory(pool, cores, model, data):
+    t, v, s, ids = data.arrays()
+    desc = model.desc_bytes()
+
+    def loglike(theta):
+        theta = np.ascontiguousarray(theta)
+        if len(theta) < 4 * cores:
+            return _cpu_block((desc, t, v, s, ids, data.n_inst, theta))
+        parts = pool.map(_cpu_block, [(desc, t, v, s, ids, data.n_inst, b)
+                                      for b in np.array_split(theta, cores)])
+        return np.concatenate(parts)
+    return loglike
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -31,10 +59,18 @@ def main():
     ap.add_argument("--epochs", type=int, default=300)
     ap.add_argument("--nlive", type=int, default=200)
     ap.add_argument("--true-planets", type=int, default=2)
+    ap.add_argument("--cpu-kmax", type=int, default=-1,
+                    help="also run the same seeded sampler on the CPU checker for k <= this")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = int(os.environ.get("LOCAL_RANK", "0"))
+    pool, cores = None, max(1, (os.cpu_count() or 1) // max(1, min(world, args.cpu_kmax + 1)))
+    if args.cpu_kmax >= 0 and any(k <= args.cpu_kmax for k in range(rank, args.kmax + 1, world)):
+        import multiprocessing as mp
+        from oracle import rv_oracle
+        rv_oracle.build()
+        pool = mp.get_context("fork").Pool(cores)  # forked before this process touches CUDA
     data = synth.make_case(2, seed=11, n_epochs=args.epochs, n_planets=args.true_planets)
     runs, logzs = [None] * (args.kmax + 1), [None] * (args.kmax + 1)
     for k in range(rank, args.kmax + 1, world):
@@ -54,9 +90,20 @@ def main():
         cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
         runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
         logzs[k] = res.logz
-        print(json.dumps({"k": k, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
-                          "seconds": time.perf_counter() - t0, "device": dev}), flush=True)
+        rec = {"k": k, "ndim": model.ndim, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
+               "seconds": time.perf_counter() - t0, "device": dev}
+        if pool is not None and k <= args.cpu_kmax:
+            t0 = time.perf_counter()
+            cpu = nested_sample(cpu_loglike_factory(pool, cores, model, data),
+                                lambda u: np.column_stack([pri[p].ppf(u[:, i]) for i, p in enumerate(model.parnames)]),
+                                model.ndim, nlive=args.nlive, seed=100 + k)
+            rec.update(cpu_logz=cpu.logz, cpu_logzerr=cpu.logzerr, cpu_ncall=cpu.ncall,
+                       cpu_seconds=time.perf_counter() - t0, cpu_cores=cores,
+                       agree_within_reported=bool(abs(cpu.logz - res.logz) <= max(cpu.logzerr, res.logzerr)))
+        print(json.dumps(rec), flush=True)
         model.close()
+    if pool is not None:
+        pool.terminate()
     if world == 1 and args.kmax >= 1:
         t, _, _, _ = data.arrays()
         nu, fapnu = fip.fip_periodogram([runs], logzs, Pmin=1.0, Pmax=1000.0, nfreq=50000,

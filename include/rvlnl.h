@@ -184,7 +184,7 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
  *               axis needs several resident ranges; 2: in place even then (through the
  *               once-per-point pass); 0: stage everything with cudaMemcpyAsync
  *   "variant"   0 optimised kernel (default), 1 conservative cross-check (IEEE division, full sin/cos)
- *   "ilp"       epochs per lane in flight, 1..4 (default 2)
+ *   "ilp"       epochs per lane in flight, 1..4; 0 (default): 4 for large batches, 2 otherwise
  *   "sched"     1 (default): graded work list -- whole points first, then the points at the end of the
  *               batch cut into 2, 4, .. "max_split" (8) sub-slices with about "phase_items" (200)
  *               percent of one item per warp in each phase, so that all warps run dry together;
@@ -306,6 +306,45 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
                       const int32_t *period_cols, const int32_t *planet_cols, int32_t K, int32_t Q,
                       double *out, double *kernel_ms);
 const char *rvl_order_last_error(void);
+
+/* ---- next row of the path: the vectorised proposal step ------------------- */
+/* Device-side bookkeeping of a population slice sampler -- the kind of step sampler the reference
+ * configures (evidence/ultranest/__init__.py:175), for k walkers at once, with every array on the
+ * device and no host read-back inside a move.  One slice move = phase 0 (direction, bracket, all
+ * stepping-out positions as candidates) -> likelihood of the k * 2 n_out candidates -> phase 1
+ * (bracket from the runs of successes; m shrinkage candidates per walker, each drawn as if the
+ * ones before it were rejected) -> likelihood of the k * m candidates -> phase 2 (accept the first
+ * candidate above *lmin; m more candidates for the walkers still pending) -> likelihood -> ... ->
+ * phase 3 (accept; walkers still pending keep their position).  The likelihood in between is
+ * rvl_transform_loglike_dev on `cand_out` (k * 2 n_out rows -> `ll_out`) after phase 0 and on
+ * `cand` (k * m rows -> `cand_th`, `cand_ll`) after phases 1 and 2.  Candidates outside the unit cube are clamped for the evaluation and never accepted.
+ * All pointers are device addresses (as 64-bit integers); random numbers are Philox4x32-10 keyed by
+ * (seed, walker) with (move, shrink_round, draw) as the counter: reproducible for a seed.
+ * evidence_b200/sampler_dev.py drives it. */
+typedef struct {
+    int32_t k, d, n_out, m;
+    uint64_t seed;
+    uint32_t move, shrink_round;
+    uint64_t lmin;    /* const double*  [1]        constraint: accept iff lnL > *lmin          */
+    uint64_t chol;    /* const double*  [d][d]     whitening (lower Cholesky factor, row major)  */
+    uint64_t u;       /* double*        [k][d]     walker positions in the unit cube (in/out)    */
+    uint64_t theta;   /* double*        [k][d]     their physical parameters (out)               */
+    uint64_t lcur;    /* double*        [k]        their lnL (out; untouched until a move lands) */
+    uint64_t dirn;    /* double*        [k][d]     scratch                                       */
+    uint64_t lo, hi, lo2, hi2; /* double* [k]      scratch                                       */
+    uint64_t tval;    /* double*        [k][m]     scratch                                       */
+    uint64_t pending; /* int32_t*       [k]        scratch                                       */
+    uint64_t cand_out;   /* double*       [k][2 n_out][d] stepping-out candidates (out of phase 0)   */
+    uint64_t inside_out; /* uint8_t*      [k][2 n_out]    scratch                                    */
+    uint64_t ll_out;     /* const double* [k][2 n_out]    their lnL (in for phase 1)                 */
+    uint64_t cand;    /* double*        [k][m][d]  shrinkage candidates (out of phases 1, 2)     */
+    uint64_t inside;  /* uint8_t*       [k][m]     scratch                                       */
+    uint64_t cand_ll; /* const double*  [k][m]     their lnL (in for phases 2, 3)                */
+    uint64_t cand_th; /* const double*  [k][m][d]  their theta                                   */
+    uint64_t stats;   /* uint64_t*      [2]        += walkers left unresolved, += accepted moves */
+} rvl_slice_args;
+int rvl_slice_phase(int32_t phase, const rvl_slice_args *args, void *stream);
+const char *rvl_slice_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def test_struct_sizes_match_the_header(built_lib):
     import tempfile
     src = ('#include <stdio.h>\n#include "rvlnl.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
            'sizeof(rvl_param),sizeof(rvl_planet_desc),sizeof(rvl_model_desc),'
-           'sizeof(rvl_prior_desc),sizeof(rvl_counters_t));return 0;}')
+           'sizeof(rvl_prior_desc),sizeof(rvl_counters_t));printf("%zu\\n",sizeof(rvl_slice_args));return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -41,7 +41,7 @@ def test_struct_sizes_match_the_header(built_lib):
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(x) for x in subprocess.check_output([exe]).split()]
     want = [ctypes.sizeof(t) for t in (_abi.rvl_param, _abi.rvl_planet_desc, _abi.rvl_model_desc,
-                                       _abi.rvl_prior_desc, _abi.rvl_counters_t)]
+                                       _abi.rvl_prior_desc, _abi.rvl_counters_t, _abi.rvl_slice_args)]
     assert got == want
 
 
