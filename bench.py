@@ -670,7 +670,7 @@ def main():
     launches0 = model.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
-    kms = []
+    kms, wms = [], []
     clocks = ClockSampler(local_rank)
     ranks.barrier()
     t_wall = time.perf_counter()
@@ -681,6 +681,8 @@ def main():
         ev[k][1].record()
         if inner_events:
             kms.append(model.last_kernel_ms())
+            if fused is not None and fused.signal == "flags":
+                wms.append(model.last_gather_wait_ms())
     ranks.barrier()
     t_wall = time.perf_counter() - t_wall
     dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
@@ -778,6 +780,13 @@ def main():
     }
     if gather_check is not None:
         line["gather_check"] = gather_check
+    if wms:  # what the exchange costs beyond the rank's own kernel (CUDA events around the wait)
+        (wmax,) = ranks.max(float(np.mean(wms)))
+        line["gather_cost"] = {"wait_after_kernel_ms_mean_rank0": float(np.mean(wms)),
+                               "wait_after_kernel_ms_mean_max_over_ranks": wmax,
+                               "nvlink_bytes_per_step_per_rank": int(8 * B * (world - 1)),
+                               "note": "time between the end of this rank's likelihood kernel and the arrival of "
+                                       "the last peer's completion flag: rank skew + NVLink latency"}
 
     # ---- parity verdict (the CPU side has been running since the start)
     if psets is not None:

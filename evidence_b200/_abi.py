@@ -102,6 +102,7 @@ SYMBOLS = {
     "rvl_counters": (c_int32, [c_void_p, POINTER(rvl_counters_t)]),
     "rvl_reset_counters": (c_int32, [c_void_p]),
     "rvl_last_kernel_ms": (c_int32, [c_void_p, _dp]),
+    "rvl_last_gather_wait_ms": (c_int32, [c_void_p, _dp]),
     "rvl_launch_count": (c_int32, [c_void_p, POINTER(c_uint64)]),
     "rvl_fp64_peak": (c_int32, [c_void_p, _dp]),
     "rvl_device_info": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32),
@@ -113,6 +114,7 @@ SYMBOLS = {
     "rvl_order_planets": (c_int32, [c_int32, _dp, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32),
                                     c_int32, c_int32, _dp, _dp]),
     "rvl_order_last_error": (c_char_p, []),
+    "rvl_post_release": (None, []),
     "rvl_slice_phase": (c_int32, [c_int32, POINTER(rvl_slice_args), c_void_p]),
     "rvl_slice_last_error": (c_char_p, []),
     "rvl_plan_describe": (c_int32, [POINTER(c_int32), c_int64, POINTER(c_int64), c_int32]),

@@ -23,6 +23,7 @@
 #include <string>
 
 #include "../../include/rvlnl.h"
+#include "rvpost.h"
 
 namespace {
 
@@ -157,6 +158,8 @@ extern "C" {
 
 const char *rvl_fip_last_error(void) { return g_fip_error.c_str(); }
 
+void rvl_post_release(void) { rvpost::release_all(); }
+
 int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int32_t nfreq,
                        const double *periods, int32_t k, const double *weights, int64_t n,
                        double pk, int32_t with_alias, double pmin, double pmax, double *fapnu,
@@ -186,25 +189,25 @@ int rvl_fip_accumulate(int32_t device, const double *nua, const double *nub, int
     if (!(wsum > 0.0L)) return fip_fail(RVL_EINVAL, "weights do not sum to a positive number");
     const double scale = pk / (double)wsum;
 
-    Buf d_nua, d_nub, d_per, d_w, d_diff, d_fap;
+    // device buffers and events are kept per device between calls (rvpost.h)
+    std::lock_guard<std::mutex> lock(rvpost::g_mutex);
+    struct { void *p; } d_nua, d_nub, d_per, d_w, d_diff, d_fap;
     const size_t gb = (size_t)nfreq * sizeof(double);
-    FCU(cudaMalloc(&d_nua.p, gb));
-    FCU(cudaMalloc(&d_nub.p, gb));
-    FCU(cudaMalloc(&d_fap.p, gb));
-    FCU(cudaMalloc(&d_diff.p, ((size_t)nfreq + 1) * sizeof(unsigned long long)));
-    FCU(cudaMalloc(&d_per.p, (size_t)n * k * sizeof(double)));
-    FCU(cudaMalloc(&d_w.p, (size_t)n * sizeof(double)));
-    FCU(cudaMemcpy(d_nua.p, nua, gb, cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_nub.p, nub, gb, cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_fap.p, fapnu, gb, cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_per.p, periods, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_w.p, weights, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-    FCU(cudaMemset(d_diff.p, 0, ((size_t)nfreq + 1) * sizeof(unsigned long long)));
+    FCU(rvpost::get(device, 0, gb, &d_nua.p));
+    FCU(rvpost::get(device, 1, gb, &d_nub.p));
+    FCU(rvpost::get(device, 2, gb, &d_fap.p));
+    FCU(rvpost::get(device, 3, ((size_t)nfreq + 1) * sizeof(unsigned long long), &d_diff.p));
+    FCU(rvpost::get(device, 4, (size_t)n * k * sizeof(double), &d_per.p));
+    FCU(rvpost::get(device, 5, (size_t)n * sizeof(double), &d_w.p));
+    FCU(cudaMemcpyAsync(d_nua.p, nua, gb, cudaMemcpyHostToDevice, 0));
+    FCU(cudaMemcpyAsync(d_nub.p, nub, gb, cudaMemcpyHostToDevice, 0));
+    FCU(cudaMemcpyAsync(d_fap.p, fapnu, gb, cudaMemcpyHostToDevice, 0));
+    FCU(cudaMemcpyAsync(d_per.p, periods, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, 0));
+    FCU(cudaMemcpyAsync(d_w.p, weights, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, 0));
+    FCU(cudaMemsetAsync(d_diff.p, 0, ((size_t)nfreq + 1) * sizeof(unsigned long long), 0));
 
-    Ev ev0, ev1;
-    FCU(cudaEventCreate(&ev0.e));
-    FCU(cudaEventCreate(&ev1.e));
-    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
+    cudaEvent_t e0, e1;
+    FCU(rvpost::events(device, &e0, &e1));
     const double two_pi = 6.283185307179586;
     const int tb = 256;
     FCU(cudaEventRecord(e0, 0));

@@ -1189,7 +1189,7 @@ struct rvl_handle {
     int sm_count = 0, smem_optin = 0, clock_khz = 0;
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;  // kernel start / end, end of the gather wait
 
     // host copies of the staged inputs
     int N = 0, Npad = 0, n_inst = 0;
@@ -1246,8 +1246,8 @@ struct rvl_handle {
 
     // bookkeeping
     uint64_t n_points = 0, n_solves = 0, launches = 0;
-    double last_ms = 0.0;
-    bool timing_pending = false;
+    double last_ms = 0.0, last_wait_ms = 0.0;
+    bool timing_pending = false, wait_pending = false;
 
     // fused all-gather: bounded wait.  status[0] = seq of the exchange that timed out (0 = none),
     // status[1] = bit mask of the ranks that never signalled; mapped host memory, written by
@@ -1686,6 +1686,11 @@ int finish_timing(rvl_t *h)
         CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->last_ms = ms;
         h->timing_pending = false;
+        if (h->wait_pending) {  // time between the end of the kernel and the last peer's signal
+            CU(h, cudaEventElapsedTime(&ms, h->ev1, h->ev2));
+            h->last_wait_ms = ms;
+            h->wait_pending = false;
+        }
     }
     return RVL_OK;
 }
@@ -1920,6 +1925,7 @@ int rvl_create(rvl_t **out, int device)
     if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
     if ((ce = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail("event", ce);
     if ((ce = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("event", ce);
+    if ((ce = cudaEventCreate(&h->ev2)) != cudaSuccess) return bail("event", ce);
     if ((ce = cudaMalloc(&h->d_counters, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail("malloc", ce);
     if ((ce = cudaMemset(h->d_counters, 0, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail("memset", ce);
     // work counters + finished-block counter: zero now, the kernel re-arms them when it ends
@@ -1999,6 +2005,7 @@ void rvl_destroy(rvl_t *h)
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -2194,6 +2201,7 @@ int rvl_loglike_dev_gather(rvl_t *h, const double *dTheta, int64_t B, double *dl
         (unsigned long long)h->opt_gather_timeout_ms * 1000000ull, h->d_status);
     CU(h, cudaGetLastError());
     ++h->launches;
+    if (h->timing_pending) { CU(h, cudaEventRecord(h->ev2, (cudaStream_t)stream)); h->wait_pending = true; }
     return RVL_OK;
 }
 
@@ -2293,6 +2301,7 @@ int rvl_loglike_gather(rvl_t *h, const double *Theta, int64_t B, double *lnL_all
         (unsigned long long)h->opt_gather_timeout_ms * 1000000ull, h->d_status);
     CU(h, cudaGetLastError());
     ++h->launches;
+    if (h->timing_pending) { CU(h, cudaEventRecord(h->ev2, h->stream)); h->wait_pending = true; }
     CU(h, cudaMemcpyAsync(lnL_all, po.ptr[rank], (size_t)n_peers * (size_t)B * sizeof(double),
                           cudaMemcpyDeviceToHost, h->stream));
     rc = hostcall_end(h, hc);
@@ -2383,11 +2392,21 @@ int rvl_last_kernel_ms(rvl_t *h, double *ms)
     }
     if (h->timing_pending) {  // *_dev launches: wait for the kernel's end event
         DevGuard g(h->device);
-        CU(h, cudaEventSynchronize(h->ev1));
+        CU(h, cudaEventSynchronize(h->wait_pending ? h->ev2 : h->ev1));
         int rc = finish_timing(h);
         if (rc) return rc;
     }
     *ms = h->last_ms;
+    return RVL_OK;
+}
+
+int rvl_last_gather_wait_ms(rvl_t *h, double *ms)
+{
+    if (!h || !ms) return RVL_EINVAL;
+    double k = 0.0;
+    const int rc = rvl_last_kernel_ms(h, &k);  // resolves the pending events
+    if (rc) return rc;
+    *ms = h->last_wait_ms;
     return RVL_OK;
 }
 

@@ -6,16 +6,18 @@
 // own planet as the source slot (new[i] = old[planets[rank(p_i)][q_i]]), which is the inverse of
 // the sorting permutation; reproduced as is (identical results on identical inputs).
 //
-// One thread per element (row, column): the K periods of the row are read (L1/L2 hits after the
-// first), the rank of the column's planet is counted (stable, NaN last: numpy's argsort order for
-// the <= 8 keys involved), and one value is gathered.  Pure byte movement: 16 B of HBM traffic per
-// element; the bound is HBM bandwidth.
+// One warp per row: the row is read ONCE, coalesced, into the warp's slice of shared memory; the K
+// periods, the "already ordered" test (:113) and the ranks come from there (broadcast reads), and
+// the row is written back coalesced through the gather.  Pure byte movement, 16 B of HBM traffic
+// per element and nothing else: the bound is HBM bandwidth.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 
 #include "../../include/rvlnl.h"
+#include "rvpost.h"
 
 namespace {
 
@@ -31,31 +33,49 @@ __device__ __forceinline__ bool before(double a, double b)
     return (a == a) && ((b != b) || a < b);
 }
 
-__global__ void order_planets_kernel(const double *in, long long n, int ndim, const OrderTab tab,
-                                     const int8_t *col_planet, const int8_t *col_pos, double *out)
+constexpr int kRowsPerBlock = 8;  // warps per block
+
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+order_planets_kernel(const double *in, long long n, int ndim, const OrderTab tab, double *out)
 {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n * ndim) return;
-    const long long row = e / ndim;
-    const int col = (int)(e - row * ndim);
-    const double *r = in + row * ndim;
-    const int p = col_planet[col];
-    int src = col;
-    if (p >= 0) {
+    __shared__ double srow[kRowsPerBlock][RVL_MAX_DIM];
+    __shared__ int8_t s_planet[RVL_MAX_DIM], s_pos[RVL_MAX_DIM];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // column -> (planet, position within the planet) from the table (K * Q entries)
+    for (int c = threadIdx.x; c < ndim; c += blockDim.x) s_planet[c] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tab.K * tab.Q; i += blockDim.x) {
+        const int p = i / tab.Q, q = i - p * tab.Q;
+        s_planet[tab.planet_col[p][q]] = (int8_t)p;
+        s_pos[tab.planet_col[p][q]] = (int8_t)q;
+    }
+    __syncthreads();
+    double *r = srow[wib];
+    const long long stride = (long long)gridDim.x * kRowsPerBlock;
+    for (long long row = (long long)blockIdx.x * kRowsPerBlock + wib; row < n; row += stride) {
+        const double *src = in + row * ndim;
+        for (int c = lane; c < ndim; c += 32) r[c] = __ldcs(src + c);  // streamed: read once
+        __syncwarp();
         double per[RVL_FIP_MAX_PLANETS];
         bool ordered = true;
         for (int j = 0; j < tab.K; ++j) {
-            per[j] = __ldg(r + tab.period_col[j]);
+            per[j] = r[tab.period_col[j]];
             if (j > 0 && !(per[j - 1] <= per[j])) ordered = false;  // :113 (NaN -> not ordered)
         }
-        if (!ordered) {
-            int rank = 0;  // position of planet p in np.argsort(periods): stable, NaN last
-            for (int j = 0; j < tab.K; ++j)
-                rank += (before(per[j], per[p]) || (j < p && !before(per[p], per[j]))) ? 1 : 0;
-            src = tab.planet_col[rank][col_pos[col]];  // :121-124
+        double *dst = out + row * ndim;
+        for (int c = lane; c < ndim; c += 32) {
+            int from = c;
+            const int p = s_planet[c];
+            if (!ordered && p >= 0) {
+                int rank = 0;  // position of planet p in np.argsort(periods): stable, NaN last
+                for (int j = 0; j < tab.K; ++j)
+                    rank += (before(per[j], per[p]) || (j < p && !before(per[p], per[j]))) ? 1 : 0;
+                from = tab.planet_col[rank][s_pos[c]];  // :121-124
+            }
+            __stcs(dst + c, r[from]);
         }
+        __syncwarp();
     }
-    out[e] = __ldg(r + src);
 }
 
 thread_local std::string g_order_error;
@@ -125,25 +145,22 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
     OCU(cudaSetDevice(device));
     struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
 
-    Buf d_in, d_out, d_pl, d_pos;
+    // device buffers and events are kept per device between calls (rvpost.h)
+    std::lock_guard<std::mutex> lock(rvpost::g_mutex);
+    struct { void *p; } d_in, d_out;
     const size_t nb = (size_t)n * ndim * sizeof(double);
-    OCU(cudaMalloc(&d_in.p, nb));
-    OCU(cudaMalloc(&d_out.p, nb));
-    OCU(cudaMalloc(&d_pl.p, RVL_MAX_DIM));
-    OCU(cudaMalloc(&d_pos.p, RVL_MAX_DIM));
-    OCU(cudaMemcpy(d_in.p, samples, nb, cudaMemcpyHostToDevice));
-    OCU(cudaMemcpy(d_pl.p, h_planet, RVL_MAX_DIM, cudaMemcpyHostToDevice));
-    OCU(cudaMemcpy(d_pos.p, h_pos, RVL_MAX_DIM, cudaMemcpyHostToDevice));
-    Ev ev0, ev1;
-    OCU(cudaEventCreate(&ev0.e));
-    OCU(cudaEventCreate(&ev1.e));
-    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
-    const long long total = (long long)n * ndim;
-    const int tb = 256;
+    OCU(rvpost::get(device, 8, nb, &d_in.p));
+    OCU(rvpost::get(device, 9, nb, &d_out.p));
+    OCU(cudaMemcpyAsync(d_in.p, samples, nb, cudaMemcpyHostToDevice, 0));
+    cudaEvent_t e0, e1;
+    OCU(rvpost::events(device, &e0, &e1));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const long long blocks_needed = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+    const unsigned grid = (unsigned)std::min<long long>(blocks_needed, (long long)sms * 8);  // resident blocks
     OCU(cudaEventRecord(e0, 0));
-    order_planets_kernel<<<(unsigned)((total + tb - 1) / tb), tb>>>(
-        (const double *)d_in.p, n, ndim, tab, (const int8_t *)d_pl.p, (const int8_t *)d_pos.p,
-        (double *)d_out.p);
+    order_planets_kernel<<<grid, kRowsPerBlock * 32>>>((const double *)d_in.p, n, ndim, tab,
+                                                      (double *)d_out.p);
     OCU(cudaEventRecord(e1, 0));
     OCU(cudaGetLastError());
     OCU(cudaMemcpy(out, d_out.p, nb, cudaMemcpyDeviceToHost));

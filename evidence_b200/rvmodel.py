@@ -380,6 +380,11 @@ class RVModel(BaseModel):
         self._check(self._lib.rvl_last_kernel_ms(self._h, byref(ms)))
         return ms.value
 
+    def last_gather_wait_ms(self):
+        ms = c_double()
+        self._check(self._lib.rvl_last_gather_wait_ms(self._h, byref(ms)))
+        return ms.value
+
     def launch_count(self):
         n = c_uint64()
         self._check(self._lib.rvl_launch_count(self._h, byref(n)))

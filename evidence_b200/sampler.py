@@ -25,7 +25,7 @@ of ``ndraw`` -- the large batches the device path is built for -- and consumed i
 for unimodal problems only.
 
 ln Z uncertainty: the larger of Skilling's estimate sqrt(H / nlive) and a bootstrap over the run's
-lineages (``lineage_bootstrap``, the estimate UltraNest's ``num_bootstraps`` makes); likelihood
+threads (``lineage_bootstrap``, the estimate UltraNest's ``num_bootstraps`` makes); likelihood
 plateaus (tied values, e.g. the model's -1e30) are retired as a whole (``retire_groups``).
 """
 import numpy as np
@@ -217,13 +217,15 @@ def retire_groups(l_sorted, n_live):
 
 def lineage_bootstrap(birth, death, root, n_roots, rng, num=30):
     """
-    Scatter of ln Z under resampling of the run's LINEAGES (what UltraNest's ``num_bootstraps``
-    estimates, evidence/ultranest/__init__.py:172): every point of a run descends from one of the
-    initial live points (its root); a bootstrap draws n_roots roots with replacement, keeps the points
-    of the drawn lineages (with multiplicity) and integrates the evidence again with the number of
-    live points that THOSE lineages had at each death.  Unlike Skilling's sqrt(H/n), which only
-    knows the shrinkage noise, this sees lineages dying out -- modes found by few live points -- which
-    is what dominates the run-to-run scatter on multimodal period posteriors.
+    Scatter of ln Z under resampling of the run's THREADS (what UltraNest's ``num_bootstraps``
+    estimates, evidence/ultranest/__init__.py:172, and nestcheck's bootstrap, Higson et al. 2018): a
+    run with n live points is n single-live-point runs merged -- the thread of a slot is the sequence
+    of points that occupied it, each born under the constraint at which its predecessor was replaced
+    (``root`` = slot).  A bootstrap draws n_roots threads with replacement, keeps their points (with
+    multiplicity) and integrates the evidence again with the number of live points THOSE threads had
+    at each death.  It contains the shrinkage noise that Skilling's sqrt(H/n) estimates and adds the
+    variance of how the posterior mass is spread over the threads; like every within-run estimate it
+    cannot see a mode that no live point ever found.
     Returns (std of ln Z over the bootstraps, the ln Z values).
     """
     birth, death = np.asarray(birth, dtype=np.float64), np.asarray(death, dtype=np.float64)
@@ -382,7 +384,7 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
                                        dlogz=dlogz, frac_remain=frac_remain, seed=seed,
                                        max_calls=max_calls, verbose=verbose, **kw)
     rng = np.random.default_rng(seed)
-    nsteps = nsteps or max(4, 2 * ndim)
+    nsteps = nsteps or max(4, 3 * ndim)  # the reference's default (evidence/ultranest/__init__.py:335)
     k = max(1, min(int(batch_fraction * nlive), nlive - 2, ndraw))
     u_live = rng.random((nlive, ndim))
     th_live = transform(u_live)
@@ -390,7 +392,7 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
     ncall = nlive
     logz, h_info, logx = -np.inf, 0.0, 0.0
     dead_theta, dead_logl, dead_logw = [], [], []
-    # lineages: the initial live point every point descends from, and the constraint it was born under
+    # threads: the slot a point occupies, and the constraint it was born under (lineage_bootstrap)
     root_live, birth_live = np.arange(nlive), np.full(nlive, -np.inf)
     dead_root, dead_birth = [], []
     niter = 0
@@ -434,7 +436,7 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
         l_new = np.where(stuck, l_live[starts], l_new)
         th_new[stuck] = th_live[starts][stuck]
         u_live[worst], th_live[worst], l_live[worst] = u_new, th_new, l_new
-        root_live[worst], birth_live[worst] = root_live[starts], lmin
+        birth_live[worst] = lmin  # (the thread of a slot continues with the point written into it)
         if ncall > max_calls:
             raise RuntimeError("nested_sample: max_calls exceeded")
         log_remain = np.max(l_live) + logx
@@ -465,8 +467,8 @@ def nested_sample(loglike, transform, ndim, nlive=400, ndraw=4096, dlogz=0.5, fr
     skilling = float(np.sqrt(max(h_info, 0.0) / nlive))
     bs_std, bs = lineage_bootstrap(dead_birth, dead_logl, dead_root, nlive,
                                    np.random.default_rng([int(seed), 0xB007]), num_bootstraps)
-    # reported uncertainty: the lineage bootstrap (which contains the shrinkage noise) where it is
-    # larger than Skilling's estimate -- on multimodal posteriors it is, several times
+    # reported uncertainty: the thread bootstrap (which contains the shrinkage noise) where it is
+    # larger than Skilling's estimate
     return NestedResult(logz=float(logz), logzerr=float(max(skilling, bs_std)),
                         logzerr_skilling=skilling, logzerr_bootstrap=bs_std,
                         ncall=int(ncall), niter=int(niter), information=float(h_info),

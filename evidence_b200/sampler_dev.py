@@ -132,10 +132,10 @@ class _NativeSlice:
     read back.  Stepping out evaluates all ``n_out`` positions of both sides at once; shrinkage runs
     ``rounds`` launches of ``m`` speculated candidates per walker (a walker whose bracket is not
     resolved after rounds * m candidates keeps its position -- counted in ``unresolved``; with the
-    defaults that is < 1e-3 of the moves).
+    defaults, 24 candidates, that is a few 1e-3 of the moves on the RV posteriors).
     """
 
-    def __init__(self, torch, k, d, dev, seed, n_out=8, m=8, rounds=2):
+    def __init__(self, torch, k, d, dev, seed, n_out=8, m=8, rounds=3):
         import ctypes
         from . import _abi
         self.torch, self.k, self.d, self.n_out, self.m, self.rounds = torch, k, d, n_out, m, rounds
@@ -200,7 +200,7 @@ class _NativeSlice:
 def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, seed=0, nsteps=None,
                          batch_fraction=0.2, speculate=None, device="cuda", max_expand=16,
                          max_shrink=64, max_calls=2_000_000_000, verbose=False, num_bootstraps=30,
-                         native=None, native_m=8, native_rounds=2, native_out=8):
+                         native=None, native_m=8, native_rounds=3, native_out=8):
     """
     Nested sampling with every array on ``device``.  ``fused(U[n, ndim]) -> (theta[n, ndim],
     lnL[n])`` maps unit-cube points to parameters and log-likelihoods on that device
@@ -219,7 +219,7 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
     gen = torch.Generator(device=dev).manual_seed(int(seed))
     if native is None:
         native = dev.type == "cuda"
-    nsteps = nsteps or max(4, 2 * ndim)
+    nsteps = nsteps or max(4, 3 * ndim)  # the reference's default (evidence/ultranest/__init__.py:335)
     k = max(1, min(int(batch_fraction * nlive), nlive - 2))
     m = max(1, min(6, 512 // k)) if speculate is None else max(1, int(speculate))
     m_out = max(m, min(max_expand, 4096 // (2 * k)))  # a likelihood launch costs the same up to ~4096 points
@@ -235,7 +235,7 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
     logx = 0.0
     logz = torch.tensor(-math.inf, dtype=f64, device=dev)
     dead_theta, dead_logl, dead_logw = [], [], []
-    # lineages (see sampler.lineage_bootstrap): root live point and birth constraint of every point
+    # threads (see sampler.lineage_bootstrap): slot and birth constraint of every point
     root_live = torch.arange(nlive, device=dev)
     birth_live = torch.full((nlive,), -math.inf, dtype=f64, device=dev)
     dead_root, dead_birth = [], []
@@ -281,8 +281,7 @@ def nested_sample_device(fused, ndim, nlive=400, dlogz=0.5, frac_remain=0.01, se
         stuck = ~torch.isfinite(l_new)  # a walker that never moved is a copy of its start point
         l_new = torch.where(stuck, l_live[starts], l_new)
         u_live[worst], th_live[worst], l_live[worst] = u_new, th_new, l_new
-        root_live[worst] = root_live[starts]
-        birth_live[worst] = lmin
+        birth_live[worst] = lmin  # (root = slot: the thread continues with the point written into it)
         if ncall > max_calls:
             raise RuntimeError("nested_sample_device: max_calls exceeded")
         # UltraNest's two criteria (evidence/ultranest/__init__.py:181-185); one read-back per round

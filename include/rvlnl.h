@@ -260,6 +260,10 @@ int rvl_reset_counters(rvl_t *h);
 /* duration (ms, CUDA events on the launching stream) of the last likelihood launch of a
  * host-buffer call, kernel only */
 int rvl_last_kernel_ms(rvl_t *h, double *ms);
+/* option "timing": time (ms) between the end of the likelihood kernel of the last fused all-gather
+ * call and the moment every peer's completion slot had arrived (the wait_flags kernel): what the
+ * exchange costs this rank beyond its own kernel -- rank skew plus NVLink latency */
+int rvl_last_gather_wait_ms(rvl_t *h, double *ms);
 /* number of kernel launches issued by this handle so far */
 int rvl_launch_count(rvl_t *h, uint64_t *n);
 /* register-resident DFMA loop: measured FP64 peak of this device, TFLOP/s (2 flop per DFMA) */
@@ -306,6 +310,9 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
                       const int32_t *period_cols, const int32_t *planet_cols, int32_t K, int32_t Q,
                       double *out, double *kernel_ms);
 const char *rvl_order_last_error(void);
+/* rvl_fip_accumulate and rvl_order_planets keep their device buffers and events per device between
+ * calls (no allocation on the second call of a size); this frees them. */
+void rvl_post_release(void);
 
 /* ---- next row of the path: the vectorised proposal step ------------------- */
 /* Device-side bookkeeping of a population slice sampler -- the kind of step sampler the reference

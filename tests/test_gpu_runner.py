@@ -22,7 +22,7 @@ def test_lnz_device_vs_cpu_oracle():
     case = _case()
     model = RVModel(case.fixedpardict, case.datadict(), case.parnames)
     model.set_priors(case.priordict)
-    kw = dict(nlive=120, seed=11, nsteps=10)
+    kw = dict(nlive=120, seed=11, nsteps=21)  # 3 ndim slice moves per point: the reference's default
     dev = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, case.ndim, **kw)
 
     # the fused u -> theta -> lnL call gives the identical run (same theta bits, same lnL bits)
@@ -72,7 +72,7 @@ def test_device_resident_sampler_matches_the_host_sampler():
     case = _case()
     model = RVModel(case.fixedpardict, case.datadict(), case.parnames)
     model.set_priors(case.priordict)
-    kw = dict(nlive=200, nsteps=12)
+    kw = dict(nlive=200, nsteps=28)  # mixed chains: profiles/r2_lnz_scatter.txt
     t0 = time.perf_counter()
     host = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, case.ndim,
                          fused=model.transform_loglike_batch, seed=3, **kw)
@@ -82,15 +82,13 @@ def test_device_resident_sampler_matches_the_host_sampler():
     dev = nested_sample_device(lambda U: model.transform_loglike_device(U), case.ndim, seed=3, **kw)
     t_dev = time.perf_counter() - t0
     assert model.counters()["n_points"] == dev.ncall
-    # The period posterior is multimodal: the run-to-run scatter of ln Z of EITHER sampler at these
-    # settings is 1.2-3.0 (tools/lnz_scatter.py: 4 seeds each, means -205.6 vs -205.8), well above
-    # the Skilling estimate (0.3) that only accounts for the shrinkage noise.  Two independent runs
-    # are therefore compared at 3 sigma of that measured scatter.
-    assert abs(dev.logz - host.logz) < 8.0, (dev.logz, host.logz)
-    # ... and the reported uncertainty now knows it: the lineage bootstrap (sampler.lineage_bootstrap)
-    assert abs(dev.logz - host.logz) <= 3.0 * np.hypot(dev.logzerr, host.logzerr)
+    # two independent samplers (numpy generator / Philox on the device): ln Z within the REPORTED
+    # uncertainties -- with mixed chains (nsteps >= 3 ndim) the run-to-run scatter is 0.2 against a
+    # reported 0.35 (profiles/r2_lnz_scatter.txt; the r1 version of this test ran 12 steps and needed 8.0)
+    assert abs(dev.logz - host.logz) <= 3.0 * np.hypot(dev.logzerr, host.logzerr), (dev.logz, host.logz)
     assert 0.1 < dev.logzerr_skilling < 1.0 and abs(dev.logzerr_skilling - host.logzerr_skilling) < 0.2
-    assert dev.method == "slice-device-native" and dev.unresolved_moves < 0.01 * dev.accepted_moves
+    assert dev.logzerr >= dev.logzerr_skilling and dev.logzerr_bootstrap > 0.05
+    assert dev.method == "slice-device-native" and dev.unresolved_moves < 0.02 * dev.accepted_moves
     per = np.median(dev.samples[:, case.parnames.index("planet1_period")])
     assert abs(per - case.truth["planet1_period"]) / case.truth["planet1_period"] < 0.02
     print(f"host-bookkeeping {t_host:.2f} s, device-resident {t_dev:.2f} s")
