@@ -26,7 +26,6 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import numpy as np  # noqa: E402
 
 from evidence_b200 import fip, priors, synth  # noqa: E402
-from evidence_b200.rvmodel import RVModel  # noqa: E402
 from evidence_b200.sampler import nested_sample  # noqa: E402
 
 _CPU = {}
@@ -37,6 +36,22 @@ def _cpu_block(args):
     from oracle import rv_oracle
     desc, t, v, s, ids, n_inst, block = args
     return rv_oracle.c_loglike_batch(desc, t, v, s, ids, n_inst, block)[0]
+
+
+class _HostModel:
+    """The model description without a device (--cpu-only): names -> slot table for the C checker."""
+
+    def __init__(self, fixed, data, parnames):
+        from evidence_b200.layout import compile_model
+        self.parnames, self.ndim = parnames, len(parnames)
+        t = data.arrays()[0]
+        self._desc, _ = compile_model(parnames, fixed, data.insts, t[0])
+
+    def desc_bytes(self):
+        return bytes(self._desc)
+
+    def close(self):
+        pass
 
 
 def cpu_loglike_factory(pool, cores, model, data):
@@ -61,6 +76,9 @@ def main():
     ap.add_argument("--true-planets", type=int, default=2)
     ap.add_argument("--cpu-kmax", type=int, default=-1,
                     help="also run the same seeded sampler on the CPU checker for k <= this")
+    ap.add_argument("--cpu-only", action="store_true",
+                    help="only the CPU checker runs (no GPU needed: the sampler is deterministic for a "
+                         "seed, so these are the CPU ln Z of the same runs made elsewhere on the device)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -82,29 +100,36 @@ def main():
         pri = {p: priors.make_prior(*v) for p, v in spec.items()}
         fixed = {f"planet{j}_epoch": synth.EPOCH for j in range(1, k + 1)}
         fixed["drift_tref"] = synth.EPOCH
-        model = RVModel(fixed, data.datadict(), list(spec), device=dev)
-        model.set_priors(pri)
-        t0 = time.perf_counter()
-        res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
-                            nlive=args.nlive, seed=100 + k, fused=model.transform_loglike_batch)
-        cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
-        runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
-        logzs[k] = res.logz
-        rec = {"k": k, "ndim": model.ndim, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
-               "seconds": time.perf_counter() - t0, "device": dev}
+        if args.cpu_only:
+            model = _HostModel(fixed, data, sorted(spec))
+            rec = {"k": k, "ndim": model.ndim}
+            res = None
+        else:
+            from evidence_b200.rvmodel import RVModel
+            model = RVModel(fixed, data.datadict(), list(spec), device=dev)
+            model.set_priors(pri)
+            t0 = time.perf_counter()
+            res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
+                                nlive=args.nlive, seed=100 + k, fused=model.transform_loglike_batch)
+            cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
+            runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
+            logzs[k] = res.logz
+            rec = {"k": k, "ndim": model.ndim, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
+                   "seconds": time.perf_counter() - t0, "device": dev}
         if pool is not None and k <= args.cpu_kmax:
             t0 = time.perf_counter()
             cpu = nested_sample(cpu_loglike_factory(pool, cores, model, data),
                                 lambda u: np.column_stack([pri[p].ppf(u[:, i]) for i, p in enumerate(model.parnames)]),
                                 model.ndim, nlive=args.nlive, seed=100 + k)
             rec.update(cpu_logz=cpu.logz, cpu_logzerr=cpu.logzerr, cpu_ncall=cpu.ncall,
-                       cpu_seconds=time.perf_counter() - t0, cpu_cores=cores,
-                       agree_within_reported=bool(abs(cpu.logz - res.logz) <= max(cpu.logzerr, res.logzerr)))
+                       cpu_seconds=time.perf_counter() - t0, cpu_cores=cores)
+            if res is not None:
+                rec["agree_within_reported"] = bool(abs(cpu.logz - res.logz) <= max(cpu.logzerr, res.logzerr))
         print(json.dumps(rec), flush=True)
         model.close()
     if pool is not None:
         pool.terminate()
-    if world == 1 and args.kmax >= 1:
+    if world == 1 and args.kmax >= 1 and not args.cpu_only:
         t, _, _, _ = data.arrays()
         nu, fapnu = fip.fip_periodogram([runs], logzs, Pmin=1.0, Pmax=1000.0, nfreq=50000,
                                         Tobs=float(t.max() - t.min()), device=dev)

