@@ -6,10 +6,12 @@
 // own planet as the source slot (new[i] = old[planets[rank(p_i)][q_i]]), which is the inverse of
 // the sorting permutation; reproduced as is (identical results on identical inputs).
 //
-// One warp per row: the row is read ONCE, coalesced, into the warp's slice of shared memory; the K
-// periods, the "already ordered" test (:113) and the ranks come from there (broadcast reads), and
-// the row is written back coalesced through the gather.  Pure byte movement, 16 B of HBM traffic
-// per element and nothing else: the bound is HBM bandwidth.
+// One block per TILE of 128 consecutive rows: the tile is one contiguous, 16-byte aligned piece of
+// memory, read ONCE with coalesced 16-byte streaming loads into shared memory; one thread per row does
+// the "already ordered" test (:113) and, for a row that fails it, permutes the planets' columns in
+// place through the ranks; the tile is written back with coalesced 16-byte stores.  16 B of HBM
+// traffic per element and ~1 instruction per element (the r1 kernel, one thread per element with its
+// own index arithmetic and K period reads, spent 8 and reached 1.1-1.4 TB/s): the bound is HBM.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,48 +35,58 @@ __device__ __forceinline__ bool before(double a, double b)
     return (a == a) && ((b != b) || a < b);
 }
 
-constexpr int kRowsPerBlock = 8;  // warps per block
+constexpr int kTileRows = 128;  // even: every tile starts on a 16-byte boundary
+constexpr int kOrderThreads = 256;
 
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
+__global__ void __launch_bounds__(kOrderThreads)
 order_planets_kernel(const double *in, long long n, int ndim, const OrderTab tab, double *out)
 {
-    __shared__ double srow[kRowsPerBlock][RVL_MAX_DIM];
-    __shared__ int8_t s_planet[RVL_MAX_DIM], s_pos[RVL_MAX_DIM];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    // column -> (planet, position within the planet) from the table (K * Q entries)
-    for (int c = threadIdx.x; c < ndim; c += blockDim.x) s_planet[c] = -1;
-    __syncthreads();
-    for (int i = threadIdx.x; i < tab.K * tab.Q; i += blockDim.x) {
-        const int p = i / tab.Q, q = i - p * tab.Q;
-        s_planet[tab.planet_col[p][q]] = (int8_t)p;
-        s_pos[tab.planet_col[p][q]] = (int8_t)q;
-    }
-    __syncthreads();
-    double *r = srow[wib];
-    const long long stride = (long long)gridDim.x * kRowsPerBlock;
-    for (long long row = (long long)blockIdx.x * kRowsPerBlock + wib; row < n; row += stride) {
-        const double *src = in + row * ndim;
-        for (int c = lane; c < ndim; c += 32) r[c] = __ldcs(src + c);  // streamed: read once
-        __syncwarp();
-        double per[RVL_FIP_MAX_PLANETS];
-        bool ordered = true;
-        for (int j = 0; j < tab.K; ++j) {
-            per[j] = r[tab.period_col[j]];
-            if (j > 0 && !(per[j - 1] <= per[j])) ordered = false;  // :113 (NaN -> not ordered)
+    extern __shared__ __align__(16) double tile[];  // [kTileRows][ndim]
+    const int tid = threadIdx.x;
+    const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long row0 = t * kTileRows;
+        const int rows = (int)min((long long)kTileRows, n - row0);
+        const long long e0 = row0 * ndim;  // first element of the tile: even, the tile is contiguous
+        const int ne = rows * ndim;
+        __syncthreads();                   // the previous tile has been written out
+        {   // (1) coalesced 16-byte streaming loads: ~1 instruction per element
+            const double2 *s2 = reinterpret_cast<const double2 *>(in + e0);
+            double2 *d2 = reinterpret_cast<double2 *>(tile);
+            for (int i = tid; i < ne / 2; i += blockDim.x) d2[i] = __ldcs(s2 + i);
+            if ((ne & 1) && tid == 0) tile[ne - 1] = __ldcs(in + e0 + ne - 1);
         }
-        double *dst = out + row * ndim;
-        for (int c = lane; c < ndim; c += 32) {
-            int from = c;
-            const int p = s_planet[c];
-            if (!ordered && p >= 0) {
-                int rank = 0;  // position of planet p in np.argsort(periods): stable, NaN last
-                for (int j = 0; j < tab.K; ++j)
-                    rank += (before(per[j], per[p]) || (j < p && !before(per[p], per[j]))) ? 1 : 0;
-                from = tab.planet_col[rank][s_pos[c]];  // :121-124
+        __syncthreads();
+        if (tid < rows) {  // (2) one thread per row: order test (:113); permute the planets in place
+            double *r = tile + (size_t)tid * ndim;
+            double per[RVL_FIP_MAX_PLANETS];
+            bool ordered = true;
+            for (int j = 0; j < tab.K; ++j) {
+                per[j] = r[tab.period_col[j]];
+                if (j > 0 && !(per[j - 1] <= per[j])) ordered = false;  // NaN -> not ordered
             }
-            __stcs(dst + c, r[from]);
+            if (!ordered) {
+                int rank[RVL_FIP_MAX_PLANETS];  // position of planet p in np.argsort(periods): stable, NaN last
+                for (int p = 0; p < tab.K; ++p) {
+                    int k = 0;
+                    for (int j = 0; j < tab.K; ++j)
+                        k += (before(per[j], per[p]) || (j < p && !before(per[p], per[j]))) ? 1 : 0;
+                    rank[p] = k;
+                }
+                for (int q = 0; q < tab.Q; ++q) {  // new[planet p][q] = old[planet rank(p)][q]  (:121-124)
+                    double v[RVL_FIP_MAX_PLANETS];
+                    for (int j = 0; j < tab.K; ++j) v[j] = r[tab.planet_col[j][q]];
+                    for (int p = 0; p < tab.K; ++p) r[tab.planet_col[p][q]] = v[rank[p]];
+                }
+            }
         }
-        __syncwarp();
+        __syncthreads();
+        {   // (3) coalesced 16-byte streaming stores
+            const double2 *s2 = reinterpret_cast<const double2 *>(tile);
+            double2 *d2 = reinterpret_cast<double2 *>(out + e0);
+            for (int i = tid; i < ne / 2; i += blockDim.x) __stcs(d2 + i, s2[i]);
+            if ((ne & 1) && tid == 0) __stcs(out + e0 + ne - 1, tile[ne - 1]);
+        }
     }
 }
 
@@ -156,11 +168,18 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
     OCU(rvpost::events(device, &e0, &e1));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const long long blocks_needed = (n + kRowsPerBlock - 1) / kRowsPerBlock;
-    const unsigned grid = (unsigned)std::min<long long>(blocks_needed, (long long)sms * 8);  // resident blocks
+    const long long n_tiles = (n + kTileRows - 1) / kTileRows;
+    const size_t smem = (size_t)kTileRows * ndim * sizeof(double);  // <= 128 KB
+    static bool opted = false;
+    if (!opted && smem > 48 * 1024) {
+        OCU(cudaFuncSetAttribute(order_planets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + 1024));
+        opted = true;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 2048)));
+    const unsigned grid = (unsigned)std::min<long long>(n_tiles, (long long)sms * per_sm);  // resident blocks
     OCU(cudaEventRecord(e0, 0));
-    order_planets_kernel<<<grid, kRowsPerBlock * 32>>>((const double *)d_in.p, n, ndim, tab,
-                                                      (double *)d_out.p);
+    order_planets_kernel<<<grid, kOrderThreads, smem>>>((const double *)d_in.p, n, ndim, tab,
+                                                       (double *)d_out.p);
     OCU(cudaEventRecord(e1, 0));
     OCU(cudaGetLastError());
     OCU(cudaMemcpy(out, d_out.p, nb, cudaMemcpyDeviceToHost));

@@ -55,6 +55,12 @@ def test_no_cpu_fallback_without_a_gpu(built_lib):
     rc = lib.rvl_create(ctypes.byref(h), -1)
     assert rc == -2 and not h.value  # RVL_ENODEV
     assert b"no CPU fallback" in lib.rvl_last_error(None)
+    # the multi-device handle and the handle-less entry points refuse just as loudly
+    rc = lib.rvl_create_multi(ctypes.byref(h), None, 0)
+    assert rc == -2 and not h.value and b"no CPU fallback" in lib.rvl_last_error(None)
+    args = _abi.rvl_slice_args()
+    args.k, args.d, args.n_out, args.m = 4, 3, 2, 2
+    assert lib.rvl_slice_phase(0, ctypes.byref(args), None) != 0
     from evidence_b200 import synth
     from evidence_b200.rvmodel import DeviceError, RVModel
     case = synth.make_case(1)
