@@ -259,6 +259,28 @@ RVL_HD void sincos_fast(const KTab &kt, double x, double &s, double &c)
 // Writing the update as "old value + small correction" keeps the added rounding error at half
 // an ulp per step however many steps are chained.
 // |d| <= 2^-10 : sin d = d - d^3/6 (next term 7e-18), 1-cos d = d^2/2 - d^4/24.   11 instr.
+// The rotation (s, c) <- (s + (c sd - s v), c - (s sd + c v)) with sd = sin d, v = 1 - cos d.
+// RVL_ROT_FUSED = 0: "old value + small correction" (mul, fma, add per component: 6 instructions,
+// one half-ulp rounding of the result); 1: s' = fma(c, sd, fma(-s, v, s)) (4 instructions, two
+// roundings of the size of the result).
+#ifndef RVL_ROT_FUSED
+#define RVL_ROT_FUSED 1
+#endif
+RVL_HD void rotate(double sd, double v, double &s, double &c)
+{
+#if RVL_ROT_FUSED
+    const double s1 = fma_(c, sd, fma_(-s, v, s));
+    const double c1 = fma_(-s, sd, fma_(-c, v, c));
+    s = s1;
+    c = c1;
+#else
+    const double ds = fma_(c, sd, -mul(s, v));
+    const double dc = fma_(s, sd, mul(c, v));
+    s = add(s, ds);
+    c = sub(c, dc);
+#endif
+}
+
 // (All the short series below use the leading coefficients of the SAME minimax kernels as
 // sincos_fast -- S1..S3, C1..C3 differ from -1/6, 1/120, .. by < 4e-16 relative, far below what
 // the truncated terms leave -- so that every sin/cos path of the Newton loop draws on one set of
@@ -269,10 +291,7 @@ RVL_HD void advance_tiny(const KTab &kt, double d, double &s, double &c)
     const double d2 = mul(d, d);
     const double sd = fma_(mul(d, d2), RVL_K(9), d);
     const double v = mul(d2, fma_(-d2, RVL_K(15), 0.5));
-    const double ds = fma_(c, sd, -mul(s, v));
-    const double dc = fma_(s, sd, mul(c, v));
-    s = add(s, ds);
-    c = sub(c, dc);
+    rotate(sd, v, s, c);
 }
 // |d| <= 2^-5 : sin d through d^7 (next 8e-20), 1-cos d through d^8 (next 2e-22).   16 instr.
 RVL_HD void advance_small(const KTab &kt, double d, double &s, double &c)
@@ -287,10 +306,7 @@ RVL_HD void advance_small(const KTab &kt, double d, double &s, double &c)
     pc = fma_(pc, d2, RVL_K(15));
     pc = fma_(pc, d2, -0.5);
     const double v = -mul(d2, pc);
-    const double ds = fma_(c, sd, -mul(s, v));
-    const double dc = fma_(s, sd, mul(c, v));
-    s = add(s, ds);
-    c = sub(c, dc);
+    rotate(sd, v, s, c);
 }
 // |d| < 0.75 (< pi/4): sin d and 1-cos d from the same minimax kernels as sincos_fast, but with
 // no range reduction and no quadrant logic.  21 FP64 instructions, no integer work.
@@ -311,10 +327,7 @@ RVL_HD void advance_medium(const KTab &kt, double d, double &s, double &c)
     pc = fma_(pc, z, RVL_K(15));
     const double sd = fma_(mul(d, z), ps, d);
     const double v = -mul(z, fma_(z, pc, -0.5));  // 1 - cos d
-    const double ds = fma_(c, sd, -mul(s, v));
-    const double dc = fma_(s, sd, mul(c, v));
-    s = add(s, ds);
-    c = sub(c, dc);
+    rotate(sd, v, s, c);
 }
 // the LAST pass of a solve: every |d| <= tol (1e-4 in the reference): sin d = d - d^3/6 (next term
 // 8e-23), 1 - cos d = d^2/2 (next term d^4/24 = 4e-18, below half an ulp of the values it is
@@ -324,10 +337,7 @@ RVL_HD void advance_final(const KTab &kt, double d, double &s, double &c)
     const double d2 = mul(d, d);
     const double sd = fma_(mul(d, d2), RVL_K(9), d);
     const double v = mul(0.5, d2);
-    const double ds = fma_(c, sd, -mul(s, v));
-    const double dc = fma_(s, sd, mul(c, v));
-    s = add(s, ds);
-    c = sub(c, dc);
+    rotate(sd, v, s, c);
 }
 constexpr int kHiFinal = 0x3F2A36E2;  // high word of 2e-4: abs_hi(d) < this  =>  |d| < 2e-4
 constexpr double kTinyStep = 0x1p-10;

@@ -7,6 +7,7 @@ from evidence_b200 import build
 VARIANTS = {
     "nopin": ["RVL_PIN_KTAB=0"],   # constants re-loaded by the compiler where it likes
     "no_fma_f": ["RVL_FMA_F=0"],   # two-rounding E - e sin E
+    "norot": ["RVL_ROT_FUSED=0"],  # rotation as old value + small correction (6 instructions)
 }
 if __name__ == "__main__":
     d = os.path.join(os.path.dirname(build.OUT), "variants")
