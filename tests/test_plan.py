@@ -95,6 +95,10 @@ CASES = [
     (313, 700, 2, {"ncol": 3, "slices": 7}),
     (32, 4096, 2, {"phase_items": 100, "max_split": 16}),
     (32, 20000, 2, {"phase_items": 50, "max_split": 4}),
+    (157, 60000, 4, {"ncol": 3, "W": 16}),   # the bench build: 4 epochs per lane, 512 threads
+    (313, 5000, 4, {"ncol": 3, "W": 16}),    # stress shape, two resident ranges, U = 4
+    (32, 4096, 3, {"W": 20}),
+    (7, 100, 4, {"W": 16}),
 ]
 
 
@@ -145,7 +149,7 @@ def test_random_plans_cover_exactly_once(built_lib):
         B = int(rng.choice([1, 2, 5, 17, 64, 100, 257, 1000]))
         if Ctot * B > 120_000:
             B = max(1, 120_000 // Ctot)
-        U = int(rng.choice([1, 2]))
+        U = int(rng.choice([1, 2, 3, 4]))
         kw = dict(W=int(rng.choice([16, 24, 28, 32])), ncol=int(rng.choice([3, 4, 6])),
                   wstride=int(rng.choice([12, 22, 40, 90])), sm=int(rng.choice([8, 132, 148])),
                   sched=int(rng.choice([0, 1])), slices=int(rng.choice([0, 0, 0, 2, 3, 9])),
