@@ -3,14 +3,25 @@ PolyChord adapter (boundary only).
 
 PolyChord calls the likelihood one point at a time from Fortran, so it cannot use large batches;
 it gets the device model through the scalar protocol (a batch of 1 per call).  The entry point,
-settings defaults and type checks follow evidence/polychord/__init__.py:32-258, 299-424.  The
-sampler itself (pypolychord, Fortran/C++) is third-party and absent from this image: importing
-this module works, ``run()`` raises ImportError without it.
+settings defaults and type checks, output attributes and pickle follow
+evidence/polychord/__init__.py:32-258, 261-297, 299-424.  The sampler itself (pypolychord,
+Fortran/C++) is third-party and absent from this image: importing this module works, ``run()``
+raises ImportError without it (the tests drive it through a test double, tests/doubles/pypolychord).
 """
 import datetime
 import os
+import pickle
+import time
+from pathlib import Path
 
 import numpy as np
+
+try:  # MPI is optional, as in the reference (:21-29)
+    from mpi4py import MPI
+    comm = MPI.COMM_WORLD
+    rank, size = comm.Get_rank(), comm.Get_size()
+except ImportError:
+    comm, rank, size = None, 0, 1
 
 
 def make_callbacks(model, priordict):
@@ -91,13 +102,62 @@ def set_polysettings(rundict, polysettings, ndim, nderived, isodate, parnames, s
 
 
 def run(model, rundict, priordict, polysettings=None):
+    """
+    ``evidence.polychord.run`` on the device model (evidence/polychord/__init__.py:32-258): same
+    signature, returns PolyChord's output object with the reference's extra attributes (:213-234) and
+    writes the same pickle (:242, 261-297).  The reference's post-processing (matplotlib) only runs
+    when ``rundict['postprocess']`` is true and the reference package is importable.
+    """
     try:
         from pypolychord import run_polychord
     except ImportError:
         raise ImportError("Install PolyChord to use this module.")
     parnames = model.parnames
-    ndim = len(parnames)
+    ndim, nderived = len(parnames), 0
     isodate = datetime.datetime.today().isoformat()
-    settings = set_polysettings(rundict, polysettings, ndim, 0, isodate, parnames)
+    if size > 1:
+        isodate = comm.bcast(isodate, root=0)
+    settings = set_polysettings(rundict, polysettings, ndim, nderived, isodate, parnames, size=size)
+    print(f'Saving results to {os.path.join(rundict.get("save_dir", ""), settings.file_root)}\n')
     prior, loglike = make_callbacks(model, priordict)
-    return run_polychord(loglike, ndim, 0, settings, prior)
+    ti = time.process_time()
+    output = run_polychord(loglike, ndim, nderived, settings, prior)
+    tf = time.process_time()
+    if size > 1:
+        ti = comm.reduce(ti, op=MPI.MIN, root=0)
+        tf = comm.reduce(tf, op=MPI.MAX, root=0)
+    if rank == 0:
+        output.make_paramnames_files([(x, x) for x in parnames])  # :203
+        output.runtime = datetime.timedelta(seconds=tf - ti)
+        output.rundict = rundict.copy()
+        output.datadict = dict(getattr(model, "datadict", {}))
+        output.fixedpardict = dict(getattr(model, "fixedpardict", {}))
+        model_path = getattr(model, "model_path", None)
+        output.model_name = str(Path(model_path).stem) if model_path else type(model).__name__
+        output.nlive = settings.nlive
+        output.nrepeats = settings.num_repeats
+        output.isodate = isodate
+        output.ncores = size
+        output.parnames = parnames
+        output.ndim = ndim
+        output.sampler = "PolyChord"
+        if hasattr(model, "counters"):  # observability added by the device path
+            output.device_counters = model.counters()
+        if "prior_names" in rundict:
+            output.priors = rundict["prior_names"]
+        if "star_params" in rundict:
+            output.starparams = rundict["star_params"]
+        print(f"\nTotal run time was: {output.runtime}")
+        dump2pickle_poly(output, output.file_root + ".pkl")
+        if rundict.get("postprocess", False):
+            from evidence.post_processing import postprocess  # the reference's own (unchanged)
+            postprocess(str(Path(output.base_dir).parent.absolute()))
+    return output
+
+
+def dump2pickle_poly(output, filename, savedir=None):
+    """Pickle PolyChord's output object next to the chains, evidence/polychord/__init__.py:261-297."""
+    pickledir = Path(output.base_dir).parent if savedir is None else savedir
+    os.makedirs(pickledir, exist_ok=True)
+    with open(os.path.join(pickledir, filename), "wb") as f:
+        pickle.dump(output, f)

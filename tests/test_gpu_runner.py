@@ -189,3 +189,31 @@ def test_ultranest_branch_on_the_device_model(tmp_path, stepsampler):
         sys.path.remove(path)
         for name in [m for m in sys.modules if m == "ultranest" or m.startswith("ultranest.")]:
             del sys.modules[name]
+
+
+def test_polychord_adapter_on_the_device_model(tmp_path):
+    """evidence.polychord.run's boundary on the DEVICE model: PolyChord's scalar callbacks (one point
+    per call: a batch of 1 through the same C-ABI entry point), reproduced by the test double of the
+    absent package; ln Z within the reported uncertainty of the vectorised sampler's."""
+    import os
+    import sys
+    from evidence_b200 import polychord as pc
+    from evidence_b200.rvmodel import RVModel
+    from evidence_b200.sampler import nested_sample
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "doubles")
+    sys.path.insert(0, path)
+    try:
+        case = _case()
+        model = RVModel(case.fixedpardict, case.datadict(pandas=True), case.parnames)
+        out = pc.run(model, {"target": "synth", "runid": "poly", "save_dir": str(tmp_path), "nplanets": 1},
+                     case.priordict, {"nlive": 100, "num_repeats": 14})
+        assert out.sampler == "PolyChord" and out.device_counters["n_points"] == out.nlike > 10000
+        model.set_priors(case.priordict)
+        ref = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, case.ndim, nlive=200,
+                            fused=model.transform_loglike_batch, seed=3, nsteps=28)
+        assert abs(out.logZ - ref.logz) <= 3.0 * np.hypot(out.logZerr, ref.logzerr) + 0.5, (out.logZ, ref.logz)
+        model.close()
+    finally:
+        sys.path.remove(path)
+        for name in [m for m in sys.modules if m == "pypolychord" or m.startswith("pypolychord.")]:
+            del sys.modules[name]

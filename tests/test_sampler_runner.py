@@ -247,3 +247,44 @@ def test_likelihood_plateau_is_retired_as_a_whole():
     assert np.isclose(dlogx[7], -1 / 3) and np.isclose(dlogx[8], -1 / 2)
     with pytest.raises(ValueError):
         retire_groups(np.array([-1.0, -1.0]), 2)
+
+
+@pytest.fixture
+def polychord_double(monkeypatch):
+    """The test double of the absent third-party package (tests/doubles/pypolychord)."""
+    import sys
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(os.path.abspath(__file__)), "doubles"))
+    for name in [m for m in sys.modules if m == "pypolychord" or m.startswith("pypolychord.")]:
+        monkeypatch.delitem(sys.modules, name)
+    import pypolychord
+    assert pypolychord.__version__.endswith("test-double")
+    yield pypolychord
+    for name in [m for m in sys.modules if m == "pypolychord" or m.startswith("pypolychord.")]:
+        sys.modules.pop(name, None)
+
+
+@pytest.mark.parametrize("ndim,want", [(1, -2.0768), (2, -4.1536)])
+def test_polychord_run_through_the_double(tmp_path, polychord_double, ndim, want):
+    """The reference's own PolyChord integration tests (tests/test_polychord.py:75-151: unit Gaussian,
+    U(-10, 10) priors, |ln Z - analytic| < 0.5, output files exist) on the adapter, with PolyChord's
+    scalar calling convention reproduced by the test double."""
+    from evidence_b200 import polychord as pc
+    model = GaussianModel(ndim)
+    calls = []
+    orig = model.log_likelihood
+    model.log_likelihood = lambda x: (calls.append(np.shape(x)), orig(x))[1]
+    priordict = {p: priors.Uniform(-10, 10) for p in model.parnames}
+    rundict = {"target": "gauss", "runid": f"poly{ndim}d", "save_dir": str(tmp_path), "nplanets": 0}
+    out = pc.run(model, rundict, priordict, {"nlive": 25 * ndim + 50, "num_repeats": 5 * ndim})
+    assert abs(out.logZ - want) < 0.5
+    assert set(calls) == {(ndim,)} and len(calls) == out.nlike       # one point per call
+    for attr in ("runtime", "rundict", "datadict", "fixedpardict", "model_name", "nlive", "nrepeats",
+                 "isodate", "ncores", "parnames", "ndim", "sampler"):
+        assert hasattr(out, attr), attr                               # :213-226 of the reference
+    assert out.sampler == "PolyChord" and out.nrepeats == 5 * ndim
+    assert out.file_root.startswith(f"gauss_poly{ndim}d_k0_nlive{25 * ndim + 50}_ncores1_polychord_")
+    assert os.path.exists(os.path.join(out.base_dir, out.file_root + ".paramnames"))
+    pkl = os.path.join(os.path.dirname(out.base_dir), out.file_root + ".pkl")
+    assert pickle.load(open(pkl, "rb")).logZ == out.logZ
+    s = pc.set_polysettings({"target": "t", "runid": "r"}, {"nlive": 10}, 3, 0, "D", ["a", "b", "c"])
+    assert s.nlive == 10 and s.num_repeats == 15 and s.base_dir.endswith("polychains")
