@@ -206,8 +206,8 @@ def test_polychord_adapter_on_the_device_model(tmp_path):
         case = _case()
         model = RVModel(case.fixedpardict, case.datadict(pandas=True), case.parnames)
         out = pc.run(model, {"target": "synth", "runid": "poly", "save_dir": str(tmp_path), "nplanets": 1},
-                     case.priordict, {"nlive": 60, "num_repeats": 10})  # ~3e5 scalar device calls
-        assert out.sampler == "PolyChord" and out.device_counters["n_points"] == out.nlike > 10000
+                     case.priordict, {"nlive": 40, "num_repeats": 7})  # ~1e5 scalar device calls
+        assert out.sampler == "PolyChord" and out.device_counters["n_points"] == out.nlike > 5000
         model.set_priors(case.priordict)
         ref = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, case.ndim, nlive=200,
                             fused=model.transform_loglike_batch, seed=3, nsteps=28)
