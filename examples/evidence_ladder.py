@@ -76,6 +76,11 @@ def main():
     ap.add_argument("--true-planets", type=int, default=2)
     ap.add_argument("--cpu-kmax", type=int, default=-1,
                     help="also run the same seeded sampler on the CPU checker for k <= this")
+    ap.add_argument("--nlive-per-dim", type=int, default=0,
+                    help="nlive = this x ndim (the reference's default is 25, evidence/ultranest/__init__.py:333)")
+    ap.add_argument("--sampler", default="host", choices=["host", "device"],
+                    help="host: numpy bookkeeping (evidence_b200.sampler); device: the device-resident "
+                         "sampler with the native bookkeeping kernels (evidence_b200.sampler_dev)")
     ap.add_argument("--cpu-only", action="store_true",
                     help="only the CPU checker runs (no GPU needed: the sampler is deterministic for a "
                          "seed, so these are the CPU ln Z of the same runs made elsewhere on the device)")
@@ -108,14 +113,22 @@ def main():
             from evidence_b200.rvmodel import RVModel
             model = RVModel(fixed, data.datadict(), list(spec), device=dev)
             model.set_priors(pri)
+            nlive = args.nlive_per_dim * model.ndim if args.nlive_per_dim else args.nlive
             t0 = time.perf_counter()
-            res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
-                                nlive=args.nlive, seed=100 + k, fused=model.transform_loglike_batch)
+            if args.sampler == "device":
+                import torch
+                from evidence_b200.sampler_dev import nested_sample_device
+                torch.cuda.set_device(dev)
+                res = nested_sample_device(model.transform_loglike_device, model.ndim, nlive=nlive,
+                                           seed=100 + k, device=f"cuda:{dev}")
+            else:
+                res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
+                                    nlive=nlive, seed=100 + k, fused=model.transform_loglike_batch)
             cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
             runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
             logzs[k] = res.logz
-            rec = {"k": k, "ndim": model.ndim, "logz": res.logz, "logzerr": res.logzerr, "ncall": res.ncall,
-                   "seconds": time.perf_counter() - t0, "device": dev}
+            rec = {"k": k, "ndim": model.ndim, "nlive": nlive, "sampler": res.method, "logz": res.logz,
+                   "logzerr": res.logzerr, "ncall": res.ncall, "seconds": time.perf_counter() - t0, "device": dev}
         if pool is not None and k <= args.cpu_kmax:
             t0 = time.perf_counter()
             cpu = nested_sample(cpu_loglike_factory(pool, cores, model, data),
