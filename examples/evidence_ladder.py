@@ -5,12 +5,11 @@ independent run per GPU -- replicas, no collective.
     python examples/evidence_ladder.py --kmax 3                      # one GPU, the k's in sequence
     torchrun --nproc-per-node 6 examples/evidence_ladder.py --kmax 5 # rank r takes k = r, r+6, ...
 
-    ... --cpu-kmax 2   # also run the SAME seeded sampler on the CPU checker for k <= 2
 
-Each line of output is one JSON record {k, logz, logzerr, ncall, seconds, device} (+ cpu_logz,
-cpu_logzerr, cpu_seconds with --cpu-kmax: the C restatement of the reference path,
-oracle/rvlnl_oracle.c, on the host cores -- test infrastructure, used here as the CPU reference
-ln Z that BASELINE.json's configs[3] asks to be printed beside the device's).  On one GPU the
+Each line of output is one JSON record {k, ndim, nlive, logz, logzerr, ncall, seconds, device}.  The
+CPU reference ln Z that BASELINE.json's configs[3] asks for beside it comes from
+tests/ladder_cpu.py (test infrastructure: the SAME seeded sampler on the CPU checker; the chains
+are identical bit for bit, profiles/r2_evidence_ladder.txt).  On one GPU the
 ladder ends with what the reference's fip_criterion.py does with such runs: p(k|y) from the
 evidences and the FIP periodogram of the posterior periods, accumulated on the device
 (evidence_b200.fip), and prints the periods where the false inclusion probability is lowest.
@@ -26,46 +25,19 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import numpy as np  # noqa: E402
 
 from evidence_b200 import fip, priors, synth  # noqa: E402
+from evidence_b200.rvmodel import RVModel  # noqa: E402
 from evidence_b200.sampler import nested_sample  # noqa: E402
 
-_CPU = {}
-
-
-def _cpu_block(args):
-    """One block of rows through the C restatement of the reference path (worker process)."""
-    from oracle import rv_oracle
-    desc, t, v, s, ids, n_inst, block = args
-    return rv_oracle.c_loglike_batch(desc, t, v, s, ids, n_inst, block)[0]
-
-
-class _HostModel:
-    """The model description without a device (--cpu-only): names -> slot table for the C checker."""
-
-    def __init__(self, fixed, data, parnames):
-        from evidence_b200.layout import compile_model
-        self.parnames, self.ndim = parnames, len(parnames)
-        t = data.arrays()[0]
-        self._desc, _ = compile_model(parnames, fixed, data.insts, t[0])
-
-    def desc_bytes(self):
-        return bytes(self._desc)
-
-    def close(self):
-        pass
-
-
-def cpu_loglike_factory(pool, cores, model, data):
-    t, v, s, ids = data.arrays()
-    desc = model.desc_bytes()
-
-    def loglike(theta):
-        theta = np.ascontiguousarray(theta)
-        if len(theta) < 4 * cores:
-            return _cpu_block((desc, t, v, s, ids, data.n_inst, theta))
-        parts = pool.map(_cpu_block, [(desc, t, v, s, ids, data.n_inst, b)
-                                      for b in np.array_split(theta, cores)])
-        return np.concatenate(parts)
-    return loglike
+def ladder_model(data, k, true_planets):
+    """(prior spec, fixed parameters) of the k-planet model on the ladder's data set."""
+    spec = {p: v for p, v in data.prior_spec.items()
+            if not p.startswith("planet") or int(p[6:p.index("_")]) <= k}
+    for j in range(true_planets + 1, k + 1):  # more planets than the data were made with
+        for nm in ("k1", "period", "ecc", "omega", "ma0"):
+            spec[f"planet{j}_{nm}"] = data.prior_spec[f"planet1_{nm}"]
+    fixed = {f"planet{j}_epoch": synth.EPOCH for j in range(1, k + 1)}
+    fixed["drift_tref"] = synth.EPOCH
+    return spec, fixed
 
 
 def main():
@@ -74,75 +46,41 @@ def main():
     ap.add_argument("--epochs", type=int, default=300)
     ap.add_argument("--nlive", type=int, default=200)
     ap.add_argument("--true-planets", type=int, default=2)
-    ap.add_argument("--cpu-kmax", type=int, default=-1,
-                    help="also run the same seeded sampler on the CPU checker for k <= this")
     ap.add_argument("--nlive-per-dim", type=int, default=0,
                     help="nlive = this x ndim (the reference's default is 25, evidence/ultranest/__init__.py:333)")
     ap.add_argument("--sampler", default="host", choices=["host", "device"],
                     help="host: numpy bookkeeping (evidence_b200.sampler); device: the device-resident "
                          "sampler with the native bookkeeping kernels (evidence_b200.sampler_dev)")
-    ap.add_argument("--cpu-only", action="store_true",
-                    help="only the CPU checker runs (no GPU needed: the sampler is deterministic for a "
-                         "seed, so these are the CPU ln Z of the same runs made elsewhere on the device)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = int(os.environ.get("LOCAL_RANK", "0"))
-    pool, cores = None, max(1, (os.cpu_count() or 1) // max(1, min(world, args.cpu_kmax + 1)))
-    if args.cpu_kmax >= 0 and any(k <= args.cpu_kmax for k in range(rank, args.kmax + 1, world)):
-        import multiprocessing as mp
-        from oracle import rv_oracle
-        rv_oracle.build()
-        pool = mp.get_context("fork").Pool(cores)  # forked before this process touches CUDA
     data = synth.make_case(2, seed=11, n_epochs=args.epochs, n_planets=args.true_planets)
     runs, logzs = [None] * (args.kmax + 1), [None] * (args.kmax + 1)
     for k in range(rank, args.kmax + 1, world):
-        spec = {p: v for p, v in data.prior_spec.items()
-                if not p.startswith("planet") or int(p[6:p.index("_")]) <= k}
-        for j in range(args.true_planets + 1, k + 1):  # more planets than the data were made with
-            for nm in ("k1", "period", "ecc", "omega", "ma0"):
-                spec[f"planet{j}_{nm}"] = data.prior_spec[f"planet1_{nm}"]
+        spec, fixed = ladder_model(data, k, args.true_planets)
         pri = {p: priors.make_prior(*v) for p, v in spec.items()}
-        fixed = {f"planet{j}_epoch": synth.EPOCH for j in range(1, k + 1)}
-        fixed["drift_tref"] = synth.EPOCH
-        if args.cpu_only:
-            model = _HostModel(fixed, data, sorted(spec))
-            rec = {"k": k, "ndim": model.ndim}
-            res = None
+        model = RVModel(fixed, data.datadict(), list(spec), device=dev)
+        model.set_priors(pri)
+        nlive = args.nlive_per_dim * model.ndim if args.nlive_per_dim else args.nlive
+        t0 = time.perf_counter()
+        if args.sampler == "device":
+            import torch
+            from evidence_b200.sampler_dev import nested_sample_device
+            torch.cuda.set_device(dev)
+            res = nested_sample_device(model.transform_loglike_device, model.ndim, nlive=nlive,
+                                       seed=100 + k, device=f"cuda:{dev}")
         else:
-            from evidence_b200.rvmodel import RVModel
-            model = RVModel(fixed, data.datadict(), list(spec), device=dev)
-            model.set_priors(pri)
-            nlive = args.nlive_per_dim * model.ndim if args.nlive_per_dim else args.nlive
-            t0 = time.perf_counter()
-            if args.sampler == "device":
-                import torch
-                from evidence_b200.sampler_dev import nested_sample_device
-                torch.cuda.set_device(dev)
-                res = nested_sample_device(model.transform_loglike_device, model.ndim, nlive=nlive,
-                                           seed=100 + k, device=f"cuda:{dev}")
-            else:
-                res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
-                                    nlive=nlive, seed=100 + k, fused=model.transform_loglike_batch)
-            cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
-            runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
-            logzs[k] = res.logz
-            rec = {"k": k, "ndim": model.ndim, "nlive": nlive, "sampler": res.method, "logz": res.logz,
-                   "logzerr": res.logzerr, "ncall": res.ncall, "seconds": time.perf_counter() - t0, "device": dev}
-        if pool is not None and k <= args.cpu_kmax:
-            t0 = time.perf_counter()
-            cpu = nested_sample(cpu_loglike_factory(pool, cores, model, data),
-                                lambda u: np.column_stack([pri[p].ppf(u[:, i]) for i, p in enumerate(model.parnames)]),
-                                model.ndim, nlive=args.nlive, seed=100 + k)
-            rec.update(cpu_logz=cpu.logz, cpu_logzerr=cpu.logzerr, cpu_ncall=cpu.ncall,
-                       cpu_seconds=time.perf_counter() - t0, cpu_cores=cores)
-            if res is not None:
-                rec["agree_within_reported"] = bool(abs(cpu.logz - res.logz) <= max(cpu.logzerr, res.logzerr))
+            res = nested_sample(model.log_likelihood_batch, model.prior_transform_batch, model.ndim,
+                                nlive=nlive, seed=100 + k, fused=model.transform_loglike_batch)
+        cols = [model.parnames.index(f"planet{j}_period") for j in range(1, k + 1)]
+        runs[k] = (res.weighted_samples[:, cols], res.weights) if k else None
+        logzs[k] = res.logz
+        rec = {"k": k, "ndim": model.ndim, "nlive": nlive, "sampler": res.method, "logz": res.logz,
+               "logzerr": res.logzerr, "ncall": res.ncall, "seconds": time.perf_counter() - t0, "device": dev}
         print(json.dumps(rec), flush=True)
         model.close()
-    if pool is not None:
-        pool.terminate()
-    if world == 1 and args.kmax >= 1 and not args.cpu_only:
+    if world == 1 and args.kmax >= 1:
         t, _, _, _ = data.arrays()
         nu, fapnu = fip.fip_periodogram([runs], logzs, Pmin=1.0, Pmax=1000.0, nfreq=50000,
                                         Tobs=float(t.max() - t.min()), device=dev)

@@ -1,8 +1,8 @@
 """Diagnostic: the bench's high-eccentricity parity set on the device (every kernel build) against
-the C port and the staged reference.  usage: python tools/diag_highecc.py [config]"""
+the C port and the staged reference.  usage: python tests/diag/diag_highecc.py [config]"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from evidence_b200 import synth
 from evidence_b200.layout import compile_model

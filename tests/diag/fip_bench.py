@@ -1,6 +1,6 @@
 # FIP-periodogram accumulation: device (rvl_fip_accumulate) vs the CPU oracle on one (run, k) block
 # of the reference's size (nfreq = 50000, evidence/fip_criterion.py:229).
-#   python tools/fip_bench.py [n_samples] [k]
+#   python tests/diag/fip_bench.py [n_samples] [k]
 import sys, time, numpy as np
 sys.path.insert(0, '.')
 from evidence_b200 import fip

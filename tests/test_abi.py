@@ -69,12 +69,14 @@ def test_no_cpu_fallback_without_a_gpu(built_lib):
 
 
 def test_product_never_imports_the_oracle():
-    """The checker is test infrastructure: nothing under evidence_b200/ may import, load or run it."""
+    """The checker is test infrastructure: nothing under evidence_b200/, examples/, tools/ or include/
+    may import, load or run it (only tests/, __graft_entry__.smoke() and bench.py's CPU legs do)."""
     pkg = os.path.join(ROOT, "evidence_b200")
     banned = re.compile(r"^\s*(from|import)\s+oracle\b|rv_oracle|librvoracle|oracle/_ref|oracle/_build|"
                         r"trueanomaly\.so|#include\s+\"[^\"]*oracle", re.M)
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".h", ".cpp")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert not banned.search(text), os.path.join(dirpath, f)
+    for top in (pkg, os.path.join(ROOT, "examples"), os.path.join(ROOT, "tools"), os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(top):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cpp", ".sh")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not banned.search(text), os.path.join(dirpath, f)

@@ -158,9 +158,9 @@ def test_gather_wait_is_bounded_and_the_handle_recovers():
 
 
 def test_evidence_ladder_one_run_per_gpu(tmp_path):
-    """BASELINE.json configs[3]: the ladder's runs are replicas, one per GPU, no collective; for
-    k <= 1 the same seeded sampler runs on the CPU checker and ln Z agrees within the reported
-    uncertainty."""
+    """BASELINE.json configs[3]: the ladder's runs are replicas, one per GPU, no collective; the same
+    seeded sampler on the CPU checker (tests/ladder_cpu.py) gives ln Z within the reported uncertainty
+    -- in fact the identical chain."""
     import json
     import subprocess
     import sys
@@ -171,12 +171,15 @@ def test_evidence_ladder_one_run_per_gpu(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(root, "examples", "evidence_ladder.py"), "--kmax", "1", "--epochs", "120",
-           "--nlive", "100", "--true-planets", "1", "--cpu-kmax", "1"]
+           "--nlive", "100", "--true-planets", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
-    recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{") and '"k"' in l]
-    assert sorted(r["k"] for r in recs) == [0, 1]
-    assert {r["device"] for r in recs} == {0, 1}  # one run per GPU
-    for r in recs:
-        assert np.isfinite(r["logz"]) and r["agree_within_reported"], r
-    assert all("cpu_logz" in r and r["cpu_cores"] >= 1 for r in recs)
+    recs = {r["k"]: r for r in (json.loads(l) for l in out.stdout.splitlines()
+                                if l.startswith("{") and '"k"' in l)}
+    assert sorted(recs) == [0, 1]
+    assert {r["device"] for r in recs.values()} == {0, 1}  # one run per GPU
+    from ladder_cpu import cpu_ladder
+    for c in cpu_ladder(1, epochs=120, nlive=100, true_planets=1):
+        r = recs[c["k"]]
+        assert np.isfinite(r["logz"]) and abs(r["logz"] - c["cpu_logz"]) <= max(r["logzerr"], c["cpu_logzerr"]), (r, c)
+        assert abs(r["logz"] - c["cpu_logz"]) < 0.05 and r["ncall"] == c["cpu_ncall"]  # the same chain

@@ -1,7 +1,7 @@
 # round 2, GPU call B (1 GPU): high-e diagnostic + the lean Newton loop A/B
 set -x
-python tools/diag_highecc.py 3 2>&1 | tail -8
-RVL_LIB=evidence_b200/variants/librvlnl_r1.so python tools/diag_highecc.py 3 2>&1 | tail -6 | sed "s/^/[r1] /"
+python tests/diag/diag_highecc.py 3 2>&1 | tail -8
+RVL_LIB=evidence_b200/variants/librvlnl_r1.so python tests/diag/diag_highecc.py 3 2>&1 | tail -6 | sed "s/^/[r1] /"
 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
 for ilp in 2 3 4; do
   python tools/prof_sweep.py 3 131072 $ilp 2>&1 | tail -1 | sed "s/^/[lean] /"

@@ -1,7 +1,7 @@
 # round 2, GPU call C (1 GPU): all GPU tests, the pinned-constant loop A/B, the bench, ncu captures
 set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/r2c_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2c_pytest_gpu.log
-python tools/diag_highecc.py 3 2>&1 | tail -7
+python tests/diag/diag_highecc.py 3 2>&1 | tail -7
 for lib in "" evidence_b200/variants/librvlnl_nopin.so; do
   tag=${lib:+nopin}; tag=${tag:-pin}
   for args in "2" "2 32" "3" "4"; do

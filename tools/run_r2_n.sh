@@ -7,4 +7,4 @@ for lib in "" evidence_b200/variants/librvlnl_nopp.so; do
   RVL_LIB=$lib python tools/prof_sweep.py 2 4096 2 2>&1 | tail -1 | sed "s/^/[$tag] /"
 done
 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -2
-python tools/diag_highecc.py 3 2>&1 | tail -5 | cut -c1-200
+python tests/diag/diag_highecc.py 3 2>&1 | tail -5 | cut -c1-200
