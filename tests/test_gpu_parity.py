@@ -223,6 +223,29 @@ def test_full_size_properties():
     m0.close()
 
 
+def test_full_size_kernel_builds_agree():
+    """BASELINE size (config 3, 131 072 theta = the batch where the automatic choice switches to
+    U = 4): the five kernel builds -- optimised with 1..4 epochs per lane, and the conservative one
+    (IEEE division, full sin/cos every step, no shortcuts) -- agree with each other to the parity bar
+    on every row.  The conservative build is the in-product cross-check of every optimisation."""
+    from evidence_b200 import synth
+    from evidence_b200.rvmodel import RVModel
+    case = synth.make_case(3)
+    m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
+    theta = case.draw_theta(131072, seed=6)
+    m.set_option("variant", 1)
+    ref = m.log_likelihood_batch(theta)
+    m.set_option("variant", 0)
+    bound = np.maximum(1e-9, 1e-13 * np.abs(ref))
+    for ilp in (0, 1, 2, 3, 4):
+        m.set_option("ilp", ilp)
+        got = m.log_likelihood_batch(theta)
+        assert np.all(np.abs(got - ref) <= bound), (ilp, float(np.max(np.abs(got - ref) / bound)))
+    c = m.counters()
+    assert c["n_cap_hits"] == 0 and c["n_invalid"] == 0
+    m.close()
+
+
 def test_config5_shape_at_scale_fused_transform():
     """BASELINE configs[4] shape (N = 1e4, K = 3) at 1e6 points through the fused u -> theta -> lnL
     device call; rows re-evaluated in small host batches must agree (bench.py runs the full 1e7)."""
