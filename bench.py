@@ -520,6 +520,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="theta per GPU and step (default: batch_for(steps))")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu baseline, sweeps, latency line, stress")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check (profiling runs)")
+    ap.add_argument("--e2e-gather", default="shared-host", choices=["shared-host", "device"],
+                    help="multi-GPU end-to-end call: lnL stored by the kernels straight into a host segment "
+                         "shared by the ranks (rvl_loglike_scatter_host; default), or gathered on the devices "
+                         "and copied back (rvl_loglike_gather)")
     ap.add_argument("--gather", default="fused", choices=["fused", "fused-barrier", "nccl"],
                     help="multi-GPU: the all-gather fused into the likelihood launch over NVLink "
                          "symmetric memory (peer stores + completion flags; default), the same with "
@@ -592,7 +596,7 @@ def main():
     theta = torch.from_numpy(theta_host).cuda()
     lnl = torch.empty(B, dtype=torch.float64, device="cuda")
     sharded = ShardedLikelihood(lambda blk: model.log_likelihood_device(blk, out=lnl), case.ndim)
-    fused = None
+    fused, shared = None, None
     gather = "none" if world == 1 else "nccl all_gather"
     if world > 1 and args.gather != "nccl":
         try:  # all-gather fused into the producing kernel over NVLink symmetric memory
@@ -647,6 +651,15 @@ def main():
                 out0 = torch.empty(world * B, dtype=torch.float64).pin_memory()
                 fused.evaluate_local_host(th_pin0.numpy(), out0.numpy())
                 gather_check["host_call_equal"] = bool(torch.equal(out0, ref_all.cpu()))
+                if args.e2e_gather == "shared-host":
+                    try:
+                        from evidence_b200.multigpu import SharedHostGather
+                        shared = SharedHostGather(model, B)
+                        got_sh = shared.evaluate_local_host(th_pin0.numpy())
+                        gather_check["shared_host_call_equal"] = bool(np.array_equal(got_sh, ref_all.cpu().numpy()))
+                    except Exception as exc:  # shared memory / registration unavailable: device gather
+                        print(f"shared-host gather unavailable ({exc!r}); using rvl_loglike_gather", file=sys.stderr)
+                        shared = None
                 del th_pin0, out0
         else:
             g1 = sharded.evaluate_local(theta)
@@ -700,10 +713,13 @@ def main():
     out_all_pin = torch.empty(B * world, dtype=torch.float64).pin_memory()
     th_np, out_np = th_pin.numpy(), out_all_pin.numpy()
     host_gather = fused is not None and fused.signal == "flags"
+    shared_out = [None]
 
     def e2e_step():
         if world == 1:
             model.log_likelihood_batch(th_np, out=out_np)  # rvl_loglike
+        elif shared is not None:
+            shared_out[0] = shared.evaluate_local_host(th_np)  # rvl_loglike_scatter_host + host flags
         elif host_gather:
             fused.evaluate_local_host(th_np, out_np)       # rvl_loglike_gather
         else:  # NCCL fallback: H2D, kernel, all-gather, D2H of the gathered vector
@@ -729,7 +745,9 @@ def main():
     gc.enable()
     e2e_ms = np.diff(np.array(marks)) * 1e3  # per call (every call ends with a stream sync)
     clk = clocks.stop()  # the sampler covers both timed regions
-    e2e_equal = bool(np.array_equal(out_np[rank * B:(rank + 1) * B], lnl.cpu().numpy())) if world == 1 or host_gather else None
+    res_np = shared_out[0] if shared_out[0] is not None else out_np
+    e2e_equal = (bool(np.array_equal(res_np[rank * B:(rank + 1) * B], lnl.cpu().numpy()))
+                 if world == 1 or host_gather or shared is not None else None)
 
     dev_ms, e2e_s = ranks.max(dev_ms, e2e_s)
 
@@ -747,7 +765,7 @@ def main():
     achieved = B * F / (k_ms * 1e-3) / 1e12
     value = world * B * K / (dev_ms * 1e-3)
     h2d = int(B * case.ndim * 8)
-    d2h = int(B * world * 8)
+    d2h = int(B * 8) if shared is not None else int(B * world * 8)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -758,6 +776,9 @@ def main():
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": ("rvl_loglike (page-locked theta read in place, lnL written in place)" if world == 1 else
+                        "rvl_loglike_scatter_host + rvl_wait_host_flags, per rank and step (page-locked theta read in "
+                        "place; every rank's kernel stores its lnL block into a host segment shared by the ranks)"
+                        if shared is not None else
                         "rvl_loglike_gather, one call per rank and step (page-locked theta read in place; gathered "
                         "lnL of all ranks copied to host memory)" if host_gather else
                         "torch copies around rvl_loglike_dev + NCCL all_gather"),
@@ -833,6 +854,8 @@ def main():
                                     "sample": "failed: " + repr(exc)}
     if pool is not None:
         pool.terminate()
+    if shared is not None:
+        shared.close()
     if rank == 0:
         emit(line)
     model.close()

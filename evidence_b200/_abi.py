@@ -96,6 +96,11 @@ SYMBOLS = {
     "rvl_loglike_gather": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64),
                                      c_int32, c_int32, c_int64, c_uint64]),
     "rvl_gather_status": (c_int32, [c_void_p]),
+    "rvl_host_register": (c_int32, [c_void_p, c_int64, POINTER(c_uint64)]),
+    "rvl_host_unregister": (c_int32, [c_void_p]),
+    "rvl_loglike_scatter_host": (c_int32, [c_void_p, c_void_p, c_int64, c_uint64, c_int64, c_int64,
+                                           c_int32, c_uint64]),
+    "rvl_wait_host_flags": (c_int32, [c_void_p, c_int32, c_uint64, c_int32]),
     "rvl_transform_loglike_dev": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                             c_void_p]),
     "rvl_trueanomaly": (c_int32, [c_void_p, _dp, c_int32, c_double, _dp, c_int32, c_double]),

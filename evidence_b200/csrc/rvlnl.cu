@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -2440,6 +2441,83 @@ int rvl_reset(rvl_t *h)
 /* 0 when no bounded wait of the fused all-gather has expired on this handle since the last check;
  * RVL_EPEER (message: the exchange number and the missing ranks) otherwise.  For the asynchronous
  * rvl_loglike_dev_gather: call it after synchronising the stream. */
+/* ---- gather through a host segment shared by the ranks' processes -------------------------------
+ * One process per GPU, HOST consumers: instead of every rank copying the whole gathered vector back
+ * (world x B doubles over each PCIe link), every rank's kernel stores ITS lnL block straight into a
+ * host memory segment that all the processes map (POSIX shared memory, registered with CUDA by each
+ * of them): B doubles per link, overlapped with the arithmetic, no device-side gather buffer, no
+ * D2H copy.  Completion: the launch's last block stores `seq` into this rank's flag slot of the same
+ * segment (system-scope release, after every block has fenced its stores); the ranks then wait for
+ * all slots on the HOST (rvl_wait_host_flags). */
+int rvl_host_register(void *ptr, int64_t bytes, uint64_t *dev_ptr)
+{
+    if (!ptr || bytes <= 0 || !dev_ptr) return fail(nullptr, RVL_EINVAL, "bad arguments");
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RVL_ECUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    void *d = nullptr;
+    e = cudaHostGetDevicePointer(&d, ptr, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(ptr); cudaGetLastError(); return fail(nullptr, RVL_ECUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e)); }
+    *dev_ptr = (uint64_t)(uintptr_t)d;
+    return RVL_OK;
+}
+
+int rvl_host_unregister(void *ptr)
+{
+    if (!ptr) return RVL_EINVAL;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RVL_ECUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+    return RVL_OK;
+}
+
+int rvl_loglike_scatter_host(rvl_t *h, const double *Theta, int64_t B, uint64_t shared_dev_ptr,
+                             int64_t offset, int64_t flag_offset, int32_t rank, uint64_t seq)
+{
+    if (!h) return RVL_EINVAL;
+    if (!h->kids.empty()) return fail(h, RVL_EINVAL, "not available on a multi-device handle");
+    if (B <= 0 || !Theta || !shared_dev_ptr || offset < 0 || flag_offset < 0 || rank < 0 || seq == 0)
+        return fail(h, RVL_EINVAL, "bad arguments");
+    if (!h->have_data || !h->have_model) return fail(h, RVL_ESTATE, "set data and model first");
+    PeerOut po{};
+    po.n = 1;
+    po.ptr[0] = reinterpret_cast<double *>((uintptr_t)shared_dev_ptr);
+    po.offset = offset;
+    po.flag_off = flag_offset;
+    po.seq = seq;
+    po.rank = rank;
+    DevGuard g(h->device);
+    HostCall hc;
+    int rc = ensure_io(h, B);
+    if (rc) return rc;
+    rc = loglike_begin(h, Theta, B, nullptr, hc, &po, h->d_lnl);
+    if (rc) return rc;
+    return hostcall_end(h, hc);
+}
+
+int rvl_wait_host_flags(const uint64_t *flags, int32_t n, uint64_t seq, int32_t timeout_ms)
+{
+    if (!flags || n < 1 || n > 4096) return RVL_EINVAL;
+    const volatile uint64_t *f = flags;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; ++i) {
+        unsigned spins = 0;
+        while (f[i] < seq) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((++spins & 0xfffu) == 0u) {
+                const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(
+                                    std::chrono::steady_clock::now() - t0).count();
+                if (timeout_ms >= 0 && ms > timeout_ms) {
+                    g_create_error = "shared-host gather timed out: rank " + std::to_string(i) + " never signalled exchange " + std::to_string((unsigned long long)seq);
+                    return RVL_EPEER;
+                }
+            }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return RVL_OK;
+}
+
 int rvl_gather_status(rvl_t *h)
 {
     if (!h) return RVL_EINVAL;

@@ -11,6 +11,10 @@ counts on every rank.
 Two ways to do the gather:
 
 * ``ShardedLikelihood`` -- the likelihood kernel, then ``all_gather_into_tensor`` (NCCL).
+* ``SharedHostGather`` -- for HOST consumers (a sampler running one process per GPU): every rank's
+  kernel stores its lnL block straight into a host memory segment shared by the ranks' processes
+  (POSIX shared memory, mapped and CUDA-registered by each of them); no device-side gathered vector,
+  no D2H copy of world x rows values per rank (``rvl_loglike_scatter_host`` / ``rvl_wait_host_flags``).
 * ``FusedGatherLikelihood`` -- the all-gather is fused into the producing kernel: the work item
   that finishes a point's lnL stores it straight into every rank's gathered vector through
   NVLink peer-mapped (symmetric) memory, and the launch's last block then stores a sequence
@@ -86,7 +90,8 @@ class FusedGatherLikelihood:
     Weak-scaling evaluator whose all-gather is fused into the likelihood kernel (see the module
     docstring).  Every rank calls ``evaluate_local(theta_block)`` with its own block of the same
     row count and receives the gathered ``lnL[world * rows]`` (a view into symmetric memory that
-    stays valid until the call after next: two buffers alternate).
+    stays valid until this rank's NEXT call: two buffers alternate, and a peer can only be two
+    exchanges ahead once this rank has entered the next one).
 
     ``signal="flags"`` (default): the launch itself tells the peers when it is done -- its last
     block stores a sequence number into a completion slot of every peer buffer, and a one-warp
@@ -159,3 +164,110 @@ class FusedGatherLikelihood:
         self.seq[k] += 1
         return self.model.log_likelihood_gather_host(theta_host, out_all_host, self.ptrs[k],
                                                      self.rank, self.flag_off, self.seq[k])
+
+
+class SharedHostGather:
+    """
+    Weak-scaling evaluator for HOST buffers whose gather goes through a host memory segment shared
+    by the ranks' processes.  Every rank calls ``evaluate_local_host(theta_host)`` with its own block
+    of ``rows`` rows (page-locked for the in-place read) and receives a numpy view ``lnL[world * rows]``
+    of the shared segment holding every rank's values (valid until this rank's NEXT call: two segments
+    alternate, and a peer can only be two exchanges ahead once this rank has entered the next one).  Per rank and step the PCIe link carries ``rows`` doubles out (plus theta in) instead
+    of ``world * rows``; the transfer overlaps the arithmetic (the kernel stores as it goes).
+    """
+
+    def __init__(self, model, rows, group=None, timeout_ms=10000):
+        import ctypes
+        from multiprocessing import shared_memory
+        import torch.distributed as dist
+        from . import _abi
+        self.model, self.rows, self.timeout_ms = model, int(rows), int(timeout_ms)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.lib = _abi.load()
+        nbytes = (self.world * self.rows + self.world) * 8
+        names = [None, None]
+        self._owned = []
+        if self.rank == 0:
+            try:
+                for k in range(2):
+                    shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                    self._owned.append(shm)
+                    names[k] = shm.name
+            except OSError:
+                names = [None, None]  # every rank raises together, below
+        dist.broadcast_object_list(names, src=0, group=group)
+        self.shm, self.data, self.flags, self.dev, self._addr, self.seq = [], [], [], [], [], [0, 0]
+        err = None
+        try:
+            if names[0] is None:
+                raise RuntimeError("rank 0 could not create the shared memory segments")
+            for k in range(2):
+                if self.rank == 0:
+                    shm = self._owned[k]
+                else:
+                    shm = shared_memory.SharedMemory(name=names[k])
+                    try:  # the creator unlinks; an attaching process must not track the segment
+                        from multiprocessing import resource_tracker
+                        resource_tracker.unregister(shm._name, "shared_memory")
+                    except Exception:  # noqa: BLE001
+                        pass
+                self.shm.append(shm)
+                arr = np.ndarray((self.world * self.rows + self.world,), dtype=np.float64, buffer=shm.buf)
+                if self.rank == 0:
+                    arr[:] = 0.0
+                self.data.append(arr[: self.world * self.rows])
+                self.flags.append(arr[self.world * self.rows:].view(np.uint64))
+                addr = arr.ctypes.data
+                dev = ctypes.c_uint64()
+                rc = self.lib.rvl_host_register(ctypes.c_void_p(addr), nbytes, ctypes.byref(dev))
+                if rc != 0:
+                    raise RuntimeError("rvl_host_register: " + self.lib.rvl_last_error(None).decode())
+                self._addr.append(addr)
+                self.dev.append(dev.value)
+        except Exception as exc:  # noqa: BLE001 -- reported after the ranks have agreed
+            err = exc
+        # the ranks succeed or fail TOGETHER (a rank that raised alone would leave the others waiting)
+        import torch
+        ok = torch.tensor([0.0 if err is not None else 1.0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok) < 1.0:
+            self.close()
+            raise RuntimeError(f"SharedHostGather unavailable on some rank ({err!r})")
+        dist.barrier(group=group)  # every rank has mapped both segments (and rank 0 zeroed them)
+        self.turn = 0
+
+    def evaluate_local_host(self, theta_host):
+        import ctypes
+        if theta_host.shape[0] != self.rows:
+            raise ValueError("SharedHostGather needs blocks of exactly `rows` rows")
+        k = self.turn
+        self.turn ^= 1
+        self.seq[k] += 1
+        m = self.model
+        rc = self.lib.rvl_loglike_scatter_host(m._h, theta_host.ctypes.data, self.rows, self.dev[k],
+                                               self.rank * self.rows, self.world * self.rows,
+                                               self.rank, self.seq[k])
+        if rc != 0:
+            m._check(rc)
+        rc = self.lib.rvl_wait_host_flags(ctypes.c_void_p(self.flags[k].ctypes.data), self.world,
+                                          self.seq[k], self.timeout_ms)
+        if rc != 0:
+            raise RuntimeError("rvl_wait_host_flags: " + self.lib.rvl_last_error(None).decode())
+        return self.data[k]
+
+    def close(self):
+        for addr in self._addr:
+            self.lib.rvl_host_unregister(__import__("ctypes").c_void_p(addr))
+        self._addr = []
+        self.data, self.flags = [], []
+        for shm in self.shm:
+            try:
+                shm.close()
+            except BufferError:
+                pass
+        for shm in self._owned:
+            try:
+                shm.unlink()
+            except FileNotFoundError:
+                pass
+        self.shm, self._owned = [], []

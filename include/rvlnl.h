@@ -248,6 +248,21 @@ int rvl_loglike_gather(rvl_t *h, const double *Theta, int64_t B, double *lnL_all
 /* after synchronising the stream of an rvl_loglike_dev_gather: RVL_EPEER if its bounded wait expired */
 int rvl_gather_status(rvl_t *h);
 
+/* The gather through a HOST segment shared by the ranks' processes (POSIX shared memory mapped by
+ * every rank; evidence_b200/multigpu.py: SharedHostGather) -- for host consumers, the cheapest form:
+ * every rank's kernel stores its B lnL values straight into the segment at element `offset`
+ * (normally rank * B) over its own PCIe link, overlapped with the arithmetic; no device-side gathered
+ * vector, no D2H copy of world * B values per rank.  When the launch has finished, `seq` is stored
+ * (release, system scope) into element `flag_offset + rank` of the segment; every process then waits
+ * on the host for all ranks' slots (rvl_wait_host_flags: RVL_EPEER after timeout_ms, < 0 = forever;
+ * message from rvl_last_error(NULL)).  rvl_host_register page-locks and maps a host range for this
+ * device context and returns its device address; each process registers its own mapping. */
+int rvl_host_register(void *ptr, int64_t bytes, uint64_t *dev_ptr);
+int rvl_host_unregister(void *ptr);
+int rvl_loglike_scatter_host(rvl_t *h, const double *Theta, int64_t B, uint64_t shared_dev_ptr,
+                             int64_t offset, int64_t flag_offset, int32_t rank, uint64_t seq);
+int rvl_wait_host_flags(const uint64_t *flags, int32_t n, uint64_t seq, int32_t timeout_ms);
+
 /* ---- the reference's own native FFI, on the device (trueanomaly.h:4) ----- */
 /* Same contract as the reference symbol except: returns -1 when ANY element hit the cap
  * (every nu[i] is still written from the last iterate, the reference leaves the rest 0). */

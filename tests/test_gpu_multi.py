@@ -57,6 +57,12 @@ def _worker(rank, world, port, ret):
         pageable = np.empty(world * rows)
         fused.evaluate_local_host(np.array(th_pin.numpy()), pageable)
         outs.append(torch.from_numpy(pageable))
+        # ... and through a host segment shared by the two processes (rvl_loglike_scatter_host)
+        from evidence_b200.multigpu import SharedHostGather
+        shared = SharedHostGather(model, rows)
+        for _ in range(4):  # alternating segments
+            outs.append(torch.from_numpy(shared.evaluate_local_host(th_pin.numpy()).copy()))
+        shared.close()
         torch.cuda.synchronize()
         ret[rank] = (want, [o.cpu().numpy() for o in outs])
         model.close()
