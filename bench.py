@@ -438,8 +438,15 @@ def latency_line(make_model, rank, world, ranks, torch, peak, gather_mode):
     th_pin = torch.from_numpy(theta_host).pin_memory()
     out_pin = torch.empty(B * world, dtype=torch.float64).pin_memory()
     th_np, out_np = th_pin.numpy(), out_pin.numpy()
+    shared = None
     if fused is not None:
-        call = lambda: fused.evaluate_local_host(th_np, out_np)
+        try:  # host consumers: the gather through a host segment shared by the ranks
+            from evidence_b200.multigpu import SharedHostGather
+            shared = SharedHostGather(model, B)
+            call = lambda: shared.evaluate_local_host(th_np)
+        except Exception as exc:  # noqa: BLE001
+            print(f"shared-host gather unavailable ({exc!r}); using rvl_loglike_gather", file=sys.stderr)
+            call = lambda: fused.evaluate_local_host(th_np, out_np)
     else:
         call = lambda: model.log_likelihood_batch(th_np, out=out_np[:B])
     for _ in range(10):
@@ -462,7 +469,11 @@ def latency_line(make_model, rank, world, ranks, torch, peak, gather_mode):
            "lnl_per_s": world * B * steps / (tot * 1e-3), "us_per_step": 1e3 * tot / steps,
            "kernel_us": 1e3 * k_ms, "frac_of_fp64_peak": B * F / (k_ms * 1e-3) / 1e12 / peak if peak else None,
            "e2e_lnl_per_s": world * B * steps / e2e_s,
+           "e2e_api": ("rvl_loglike" if world == 1 else
+                       "rvl_loglike_scatter_host + rvl_wait_host_flags" if shared is not None else "rvl_loglike_gather"),
            "e2e_us_per_call_percentiles_1_50_99": [float(x) for x in np.percentile(us, [1, 50, 99])]}
+    if shared is not None:
+        shared.close()
     model.close()
     return res
 
