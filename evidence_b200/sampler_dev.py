@@ -168,10 +168,19 @@ class _NativeSlice:
             raise RuntimeError("rvl_slice_phase: " + self.lib.rvl_slice_last_error().decode())
 
     @staticmethod
-    def _eval(fused, pts, th_out, ll_out):
-        try:  # a device callable that writes in place (RVModel.transform_loglike_device)
+    def _writes_in_place(fused):
+        """Does ``fused`` take ``theta=`` / ``lnl=`` output tensors (RVModel.transform_loglike_device)?"""
+        import inspect
+        try:
+            params = inspect.signature(fused).parameters
+        except (TypeError, ValueError):
+            return False
+        return "theta" in params and "lnl" in params
+
+    def _eval(self, fused, pts, th_out, ll_out):
+        if self._inplace:
             fused(pts, theta=th_out, lnl=ll_out)
-        except TypeError:
+        else:
             th, ll = fused(pts)
             th_out.copy_(th)
             ll_out.copy_(ll)
@@ -179,6 +188,7 @@ class _NativeSlice:
     def moves(self, fused, u, theta, lcur, lmin, chol, nsteps):
         """nsteps slice moves of the k walkers u (updated in place with theta and lcur)."""
         a = self.args
+        self._inplace = self._writes_in_place(fused)
         chol = chol.contiguous()
         a.lmin, a.chol = lmin.data_ptr(), chol.data_ptr()
         a.u, a.theta, a.lcur = u.data_ptr(), theta.data_ptr(), lcur.data_ptr()
