@@ -102,14 +102,6 @@ int ofail(int code, const std::string &msg)
         if (e_ != cudaSuccess)                                                                  \
             return ofail(RVL_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
     } while (0)
-struct Buf {
-    void *p = nullptr;
-    ~Buf() { if (p) cudaFree(p); }
-};
-struct Ev {  // released on every return path, like Buf
-    cudaEvent_t e = nullptr;
-    ~Ev() { if (e) cudaEventDestroy(e); }
-};
 
 }  // namespace
 
@@ -130,8 +122,8 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
     OrderTab tab{};
     tab.K = K;
     tab.Q = Q;
-    int8_t h_planet[RVL_MAX_DIM], h_pos[RVL_MAX_DIM];
-    for (int i = 0; i < RVL_MAX_DIM; ++i) { h_planet[i] = -1; h_pos[i] = 0; }
+    int8_t h_planet[RVL_MAX_DIM];
+    for (int i = 0; i < RVL_MAX_DIM; ++i) h_planet[i] = -1;
     for (int p = 0; p < K; ++p) {
         if (period_cols[p] < 0 || period_cols[p] >= ndim) return ofail(RVL_EINVAL, "period column out of range");
         tab.period_col[p] = period_cols[p];
@@ -141,7 +133,6 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
             if (h_planet[c] >= 0) return ofail(RVL_EINVAL, "a column belongs to two planets");
             tab.planet_col[p][q] = c;
             h_planet[c] = (int8_t)p;
-            h_pos[c] = (int8_t)q;
         }
     }
     if (n == 0) return RVL_OK;
@@ -170,10 +161,10 @@ int rvl_order_planets(int32_t device, const double *samples, int64_t n, int32_t 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const long long n_tiles = (n + kTileRows - 1) / kTileRows;
     const size_t smem = (size_t)kTileRows * ndim * sizeof(double);  // <= 128 KB
-    static bool opted = false;
-    if (!opted && smem > 48 * 1024) {
+    static uint64_t opted = 0;  // one bit per device: the attribute belongs to the device's context
+    if (smem > 48 * 1024 && !(device < 64 && (opted >> device & 1))) {
         OCU(cudaFuncSetAttribute(order_planets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + 1024));
-        opted = true;
+        if (device < 64) opted |= 1ull << device;
     }
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 2048)));
     const unsigned grid = (unsigned)std::min<long long>(n_tiles, (long long)sms * per_sm);  // resident blocks
