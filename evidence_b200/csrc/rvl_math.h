@@ -162,25 +162,28 @@ RVL_HD double rcp(double x)
         2.48015872894767294178e-05,    /* 13  C3                      */                         \
         -1.38888888888741095749e-03,   /* 14  C2                      */                         \
         4.16666666666666019037e-02,    /* 15  C1                      */                         \
-        0.999999                       /* 16  multiplier of the FP64 peak probe */                         \
+        0.999999,                      /* 16  multiplier of the FP64 peak probe */                         \
+        4.21626984126984127e-04,       /* 17  17/40320: d^7 of tan(d/2) */                       \
+        4.16666666666666667e-03        /* 18  1/240:    d^5 of tan(d/2) */                       \
     }
 // The functions below take the table as their first argument (`kt`): the likelihood kernel
 // loads it ONCE per thread into (uniform) registers with loads the compiler may not
 // rematerialise, so that the Newton loop holds no constant loads at all -- FP64 instructions of
 // sm_100a take register or uniform-register operands only, never a constant-bank address, and
 // ptxas otherwise re-loads each path's coefficients on every pass (18 loads per Kepler solve).
+constexpr int kKTab = 19;
 struct KTab {
-    double v[17];
+    double v[kKTab];
     int vz;  // device: an opaque per-thread zero (see RVL_KV); host: unused
 };
 static const KTab h_ktab = {RVL_K_TABLE, 0};
 #if defined(__CUDACC__)
-__constant__ double d_ktab[17] = RVL_K_TABLE;
+__constant__ double d_ktab[kKTab] = RVL_K_TABLE;
 __device__ __forceinline__ KTab load_ktab()
 {
     KTab k;
 #pragma unroll
-    for (int i = 0; i < 17; ++i) k.v[i] = d_ktab[i];
+    for (int i = 0; i < kKTab; ++i) k.v[i] = d_ktab[i];
     // zero in every lane (lanemask_lt < 2^31), but a per-lane value for the assembler
     asm volatile("mov.u32 %0, %%lanemask_lt;\n\tshr.u32 %0, %0, 31;" : "=r"(k.vz));
     return k;
@@ -195,7 +198,7 @@ __device__ __forceinline__ KTab load_ktab_pinned()
     asm volatile("mov.u32 %0, %%smid;\n\tshr.u32 %0, %0, 16;" : "=r"(uz));
     const size_t base = __cvta_generic_to_constant(d_ktab) + (size_t)uz * 8u;
 #pragma unroll
-    for (int i = 0; i < 17; ++i)
+    for (int i = 0; i < kKTab; ++i)
         asm volatile("ld.const.f64 %0, [%1];" : "=d"(k.v[i]) : "l"(base + 8u * i));
     // zero in every lane (lanemask_lt < 2^31), but a per-lane value for the assembler
     asm volatile("mov.u32 %0, %%lanemask_lt;\n\tshr.u32 %0, %0, 31;" : "=r"(k.vz));
@@ -281,6 +284,22 @@ RVL_HD void rotate(double sd, double v, double &s, double &c)
 #endif
 }
 
+// The same rotation as THREE shears, in place: with t = tan(d/2),
+//   [cos d  sin d; -sin d  cos d] = [1 t; 0 1] [1 0; -sin d 1] [1 t; 0 1]
+// (1 - t sin d = cos d, t (1 + cos d) = sin d).  3 FP64 instructions instead of 4 and no register
+// move (each step overwrites the operand it no longer needs; the 4-FMA form needs the old s for
+// c' and the old c for s').  Every step is "old value + small correction": half an ulp of the
+// result per step.  Used where tan(d/2) is as short a series as 1 - cos d (|d| <= 2^-5).
+#ifndef RVL_ROT_SHEAR
+#define RVL_ROT_SHEAR 1
+#endif
+RVL_HD void rotate_shear(double t, double sd, double &s, double &c)
+{
+    s = fma_(t, c, s);
+    c = fma_(-sd, s, c);
+    s = fma_(t, c, s);
+}
+
 // (All the short series below use the leading coefficients of the SAME minimax kernels as
 // sincos_fast -- S1..S3, C1..C3 differ from -1/6, 1/120, .. by < 4e-16 relative, far below what
 // the truncated terms leave -- so that every sin/cos path of the Newton loop draws on one set of
@@ -289,9 +308,17 @@ RVL_HD void rotate(double sd, double v, double &s, double &c)
 RVL_HD void advance_tiny(const KTab &kt, double d, double &s, double &c)
 {
     const double d2 = mul(d, d);
+#if RVL_ROT_SHEAR
+    // tan(d/2) = d/2 + d^3/24 (next term d^5/240 < 4e-18); sin d = d - d^3/6 (next 8e-18)
+    const double d3 = mul(d, d2);
+    const double sd = fma_(d3, RVL_K(9), d);
+    const double t = fma_(d3, RVL_K(15), mul(0.5, d));
+    rotate_shear(t, sd, s, c);
+#else
     const double sd = fma_(mul(d, d2), RVL_K(9), d);
     const double v = mul(d2, fma_(-d2, RVL_K(15), 0.5));
     rotate(sd, v, s, c);
+#endif
 }
 // |d| <= 2^-5 : sin d through d^7 (next 8e-20), 1-cos d through d^8 (next 2e-22).   16 instr.
 RVL_HD void advance_small(const KTab &kt, double d, double &s, double &c)
@@ -300,6 +327,16 @@ RVL_HD void advance_small(const KTab &kt, double d, double &s, double &c)
     double ps = RVL_KV(7);
     ps = fma_(ps, d2, RVL_K(8));
     ps = fma_(ps, d2, RVL_K(9));
+#if RVL_ROT_SHEAR
+    // tan(d/2) = d/2 + d^3/24 + d^5/240 + 17 d^7/40320 (next term 31 d^9/725760 < 2e-18)
+    const double d3 = mul(d, d2);
+    const double sd = fma_(d3, ps, d);
+    double pt = RVL_KV(17);
+    pt = fma_(pt, d2, RVL_K(18));
+    pt = fma_(pt, d2, RVL_K(15));
+    const double t = fma_(d3, pt, mul(0.5, d));
+    rotate_shear(t, sd, s, c);
+#else
     const double sd = fma_(mul(d, d2), ps, d);
     double pc = RVL_KV(13);
     pc = fma_(pc, d2, RVL_K(14));
@@ -307,6 +344,7 @@ RVL_HD void advance_small(const KTab &kt, double d, double &s, double &c)
     pc = fma_(pc, d2, -0.5);
     const double v = -mul(d2, pc);
     rotate(sd, v, s, c);
+#endif
 }
 // |d| < 0.75 (< pi/4): sin d and 1-cos d from the same minimax kernels as sincos_fast, but with
 // no range reduction and no quadrant logic.  21 FP64 instructions, no integer work.
@@ -334,10 +372,14 @@ RVL_HD void advance_medium(const KTab &kt, double d, double &s, double &c)
 // subtracted from).  10 instructions.  Valid for |d| < 2e-4.
 RVL_HD void advance_final(const KTab &kt, double d, double &s, double &c)
 {
+#if RVL_ROT_SHEAR
+    advance_tiny(kt, d, s, c);  // (the tiny series holds up to 2^-10; same instruction count)
+#else
     const double d2 = mul(d, d);
     const double sd = fma_(mul(d, d2), RVL_K(9), d);
     const double v = mul(0.5, d2);
     rotate(sd, v, s, c);
+#endif
 }
 constexpr int kHiFinal = 0x3F2A36E2;  // high word of 2e-4: abs_hi(d) < this  =>  |d| < 2e-4
 constexpr double kTinyStep = 0x1p-10;

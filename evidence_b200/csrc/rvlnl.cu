@@ -304,8 +304,8 @@ __device__ __forceinline__ void solve_planet_ref(const rvl::KTab &kt, const doub
     for (int u = 0; u < U; ++u) {
         iters[u] += last[u] - 1;
         caps += (fabs(d[u]) > tol) ? 1 : 0;
-        rv[u] = VARIANT == 0 ? rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec)
-                             : rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce);
+        rv[u] = rvl::add(rv[u], VARIANT == 0 ? rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec)
+                                             : rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce));
     }
 }
 
@@ -386,7 +386,19 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
 #pragma unroll
                 for (int u = 0; u < U; ++u) rvl::sincos_fast(kt, E[u], s[u], c[u]);
             }
-            if (trip >= itmax) break;  // the cap (trueanomaly.c:32-33)
+            if (trip >= itmax) {  // the cap (trueanomaly.c:32-33): rare, finished on the spot so that
+                                  // the common exit below is reached from the last pass alone and
+                                  // takes (sin E, cos E) from where that pass left them (no moves)
+                const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
+                const double mAec = lds_f64(pc + 56);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    caps += (fabs(d[u]) > tol) ? 1 : 0;
+                    iters[u] += last[u] - 1;
+                    rv[u] = rvl::add(rv[u], rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec));
+                }
+                return;
+            }
             ++trip;
             // (2) one Newton step (trueanomaly.c:25-29); frozen lanes (|d| <= tol, :21) get r = 0
 #pragma unroll
@@ -415,14 +427,10 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
     }
     const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
     const double mAec = lds_f64(pc + 56);
-    if (trip >= itmax) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) caps += (fabs(d[u]) > tol) ? 1 : 0;
-    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         iters[u] += last[u] - 1;
-        rv[u] = rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec);
+        rv[u] = rvl::add(rv[u], rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec));
     }
 }
 
@@ -524,15 +532,26 @@ struct ItemSums {
 #ifndef RVL_OUTLINE
 #define RVL_OUTLINE 0
 #endif
+#ifndef RVL_PIN_WC
+#define RVL_PIN_WC 1
+#endif
 #if RVL_OUTLINE
 #define RVL_ITEM_INLINE __noinline__
 #else
 #define RVL_ITEM_INLINE __forceinline__
 #endif
 template <int VARIANT, int U>
-__device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCtx *hc, uint32_t a_wc,
+__device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCtx *hc, uint32_t a_wc_in,
                                                 int c_lo, int c_hi, int lane)
 {
+#if RVL_PIN_WC
+    // the address of the warp's constants is needed once per planet and epoch group; left to
+    // itself ptxas re-derives it from %tid, the cluster rank and kernel parameters every time (19
+    // instructions) rather than hold one register.  The result of a shuffle cannot be re-derived.
+    const uint32_t a_wc = __shfl_sync(kFull, a_wc_in, 0);
+#else
+    const uint32_t a_wc = a_wc_in;
+#endif
     const double tol = hc->tol;
     const int K = hc->K, itmax = hc->itmax, drift_hi = hc->drift_hi, nlin = hc->nlin, N = hc->N;
     const bool has_drift = hc->has_drift != 0;
@@ -564,11 +583,10 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
         }
         int cap_l = 0;
         for (int p = 0; p < K; ++p) {
-            double v[U];
+            // each solve ADDS its planet's velocity to rvsum (kep_rv :383: the planets' sum, first
+            // to last; 0 + v is v)
             solve_planet<VARIANT, U>(kt, t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
-                                     itmax, v, it_l, cap_l);
-#pragma unroll
-            for (int u = 0; u < U; ++u) rvsum[u] = (p == 0) ? v[u] : rvl::add(rvsum[u], v[u]);
+                                     itmax, rvsum, it_l, cap_l);
         }
         caps += cap_l;  // (padded / repeated lanes included: a cap hit is a cap hit)
 #pragma unroll
