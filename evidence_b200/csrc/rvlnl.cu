@@ -83,6 +83,7 @@ struct KArgs {
     long long B;
     long long ptS0;  // first point that is split into more than one item
     double cte;      // -0.5 N ln(2 pi)
+    double tlo, thi; // range of the epochs (point_setup: is every mean anomaly in the fast range?)
     int N, Npad, ncol;
     int Sm, cpm;     // resident epoch ranges ("memory slices": block b holds range b % Sm), chunks each
     unsigned nitems; // compute items per queue
@@ -173,6 +174,12 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ int lds_u8(uint32_t addr)
 {
     uint32_t v;
@@ -219,8 +226,11 @@ __device__ __forceinline__ bool any_big(const double (&E)[U])
 template <int VARIANT, int U>
 __device__ __forceinline__ void solve_planet_ref(const rvl::KTab &kt, const double (&t)[U], uint32_t pc, double tol,
                                                  int itmax, double (&rv)[U], int (&iters)[U],
-                                                 int &caps)
+                                                 int &caps, int done = 1)
 {
+    // `done`: Newton steps whose iteration counts the caller has already added (the lean loop
+    // hands over after `done` steps; a lane is active in steps 1..last, so what is left to add is
+    // max(last - done, 0)); 1 = only the first step, which the caller of solve_planet counts
     const double nmot = lds_f64(pc), M0 = lds_f64(pc + 8), ec = lds_f64(pc + 16),
                  epoch = lds_f64(pc + 48);
     double M[U], E[U], s[U], c[U], d[U];
@@ -302,7 +312,7 @@ __device__ __forceinline__ void solve_planet_ref(const rvl::KTab &kt, const doub
     const double mAec = lds_f64(pc + 56);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        iters[u] += last[u] - 1;
+        iters[u] += max(last[u] - done, 0);
         caps += (fabs(d[u]) > tol) ? 1 : 0;
         rv[u] = rvl::add(rv[u], VARIANT == 0 ? rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec)
                                              : rvl::kepler_rv(s[u], c[u], ec, A, Bs, Ce));
@@ -327,7 +337,7 @@ __device__ __forceinline__ void solve_planet_ref(const rvl::KTab &kt, const doub
 template <int VARIANT, int U>
 __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (&t)[U], uint32_t pc, double tol,
                                              int itmax, double (&rv)[U], int (&iters)[U],
-                                             int &caps)
+                                             int &caps, bool lean)
 {
     if (VARIANT != 0) {
         solve_planet_ref<VARIANT, U>(kt, t, pc, tol, itmax, rv, iters, caps);
@@ -337,15 +347,11 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
                  epoch = lds_f64(pc + 48);
     const int tol_hi = __double2hiint(tol);
     double M[U], E[U], s[U], c[U], d[U];
-    int last[U];  // last Newton step in which the lane was active
-    bool big = false;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        M[u] = rvl::mean_anomaly(nmot, t[u], epoch, M0);
-        big = big || !(abs_hi(M[u]) < kHiTrigMax);
-        last[u] = 1;
-    }
-    bool fallback = __any_sync(kFull, big || !(ec >= -0.99)) || !(tol_hi < rvl::kHiFinal) || itmax < 2;
+    for (int u = 0; u < U; ++u) M[u] = rvl::mean_anomaly(nmot, t[u], epoch, M0);
+    // `lean` (warp-uniform, decided once per point by point_setup and item_epochs): every |M| of
+    // the point is inside the fast sin/cos range, e >= -0.99, the reference tolerance, itmax >= 2
+    bool fallback = !lean;
     int trip = 1;
     if (!fallback) {
         // pass 1 + step 1: E0 = M, every lane active (trueanomaly.c:19-29)
@@ -394,7 +400,6 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     caps += (fabs(d[u]) > tol) ? 1 : 0;
-                    iters[u] += last[u] - 1;
                     rv[u] = rvl::add(rv[u], rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec));
                 }
                 return;
@@ -403,10 +408,20 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
             // (2) one Newton step (trueanomaly.c:25-29); frozen lanes (|d| <= tol, :21) get r = 0
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool pa = fabs(d[u]) > tol;
                 const double x = rvl::fma_(-ec, c[u], 1.0);
                 const double y0 = rvl::rcp_seed(x);
-                const double y = __hiloint2double(pa ? __double2hiint(y0) : 0, 0);
+                // pa = |d| > tol (false for NaN, like the reference's test): the seed's high word
+                // or 0, and the iteration count as ONE predicated add (a lane is active in steps
+                // 1..k, so the count is k; the compiler's own form is an add plus a select)
+                int yh;
+                asm("{\n\t.reg .pred p;\n\t.reg .f64 a;\n\t"
+                    "abs.f64 a, %3;\n\t"
+                    "setp.gt.f64 p, a, %4;\n\t"
+                    "selp.b32 %0, %2, 0, p;\n\t"
+                    "@p add.s32 %1, %1, 1;\n\t}"
+                    : "=r"(yh), "+r"(iters[u])
+                    : "r"(__double2hiint(y0)), "d"(d[u]), "d"(tol));
+                const double y = __hiloint2double(yh, 0);
                 const double e = rvl::fma_(-x, y, 1.0);
                 const double r = rvl::fma_(y, rvl::fma_(e, e, e), y);
 #if RVL_FMA_F
@@ -417,21 +432,17 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
                 const double En = rvl::fma_(-f, r, E[u]);
                 d[u] = rvl::sub(En, E[u]);  // exact; 0 for a frozen lane
                 E[u] = En;
-                last[u] = pa ? trip : last[u];  // (one select with a uniform operand)
             }
         }
     }
     if (fallback) {  // (warp-uniform) restart in the general loop: same arithmetic, same trajectory
-        solve_planet_ref<0, U>(kt, t, pc, tol, itmax, rv, iters, caps);
+        solve_planet_ref<0, U>(kt, t, pc, tol, itmax, rv, iters, caps, trip);
         return;
     }
     const double A = lds_f64(pc + 24), Bs = lds_f64(pc + 32), Ce = lds_f64(pc + 40);
     const double mAec = lds_f64(pc + 56);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        iters[u] += last[u] - 1;
-        rv[u] = rvl::add(rv[u], rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec));
-    }
+    for (int u = 0; u < U; ++u) rv[u] = rvl::add(rv[u], rvl::kepler_rv2(s[u], c[u], ec, A, Bs, Ce, mAec));
 }
 
 // ---- per-point setup: theta row -> per-warp constants (modelk :411-457, :181-192) ---------
@@ -446,10 +457,11 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
 #define RVL_SETUP_INLINE __forceinline__
 #endif
 __device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const double *row,
-                                            double *wc, int lane)
+                                            double *wc, int lane, double tlo, double thi)
 {
     const int K = m.n_planets;
     bool bad = false;
+    bool lean = true;  // this planet's solves may take the lean Newton loop (see solve_planet)
     const rvl::KTab kt = rvl::load_ktab();
     if (lane < K) {
         const rvl_planet_desc &pl = m.planet[lane];
@@ -492,6 +504,11 @@ __device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const doub
         pc[5] = rvl::mul(amp, rvl::mul(ecc, cw));
         pc[6] = par_of(pl.epoch, row);
         pc[7] = -rvl::mul(pc[3], ec);
+        // |M| <= |n| max|t - epoch| + |M0| over the data set's epochs (padding repeats an epoch):
+        // below the fast sin/cos range for every epoch, or the point takes the general loop.
+        // NaN / Inf anywhere compares false.
+        const double span = fmax(fabs(rvl::sub(tlo, pc[6])), fabs(rvl::sub(thi, pc[6])));
+        lean = rvl::add(rvl::mul(fabs(pc[0]), span), fabs(M0)) < 0.99 * rvl::kTrigFastMax && ec >= -0.99;
     }
     double *ic = wc + K * kPlanetStride;
     if (lane < m.n_inst) {
@@ -506,6 +523,8 @@ __device__ RVL_SETUP_INLINE bool point_setup(const rvl_model_desc &m, const doub
     double *dc = ic + 2 * m.n_inst;
     if (lane < 4) dc[lane] = m.drift_in_model ? par_of(m.drift[lane], row) : 0.0;
     if (lane < m.n_linpar) dc[4 + lane] = par_of(m.linpar[lane], row);
+    lean = __all_sync(kFull, lean);
+    if (lane == 0) dc[4 + m.n_linpar] = lean ? 1.0 : 0.0;
     __syncwarp();
     return !__any_sync(kFull, bad);
 }
@@ -562,6 +581,9 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
     const uint32_t a_inst = hc->a_inst0 + (uint32_t)lane;
     const uint32_t lin0 = hc->lin0;
     const int e_base = hc->e_base0 + lane;
+    // the lean Newton loop: the point's flag (point_setup) and the launch-wide conditions
+    const bool lean = lds_u32(a_dc + 32u + (uint32_t)nlin * 8u + 4u) != 0u &&
+                      __double2hiint(tol) < rvl::kHiFinal && itmax >= 2;
     double chi = 0.0, prod = 1.0;
     int esum = 0, iters = 0, caps = 0;
     bool ok = true;
@@ -586,7 +608,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             // each solve ADDS its planet's velocity to rvsum (kep_rv :383: the planets' sum, first
             // to last; 0 + v is v)
             solve_planet<VARIANT, U>(kt, t, a_wc + (uint32_t)(p * kPlanetStride) * 8u, tol,
-                                     itmax, rvsum, it_l, cap_l);
+                                     itmax, rvsum, it_l, cap_l, lean);
         }
         caps += cap_l;  // (padded / repeated lanes included: a cap hit is a cap hit)
 #pragma unroll
@@ -776,7 +798,7 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
         if (lane == 0) next = atomicAdd(&a.work[sl], 1u);
         const long long pt = a.ptS0 + (long long)idx;
         stage_row(a.theta + pt * m.ndim);
-        const bool valid = point_setup(m, srow, a.gconsts + (size_t)idx * a.wstride, lane);
+        const bool valid = point_setup(m, srow, a.gconsts + (size_t)idx * a.wstride, lane, a.tlo, a.thi);
         __threadfence();
         __syncwarp();
         if (lane == 0) st_release_u32(a.ready + idx, a.seq * 2u + (valid ? 0u : 1u));
@@ -825,7 +847,7 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
             valid = __all_sync(kFull, (pf_flag & 1u) == 0u);
         } else {
             stage_row(row);
-            valid = point_setup(m, srow, wc, lane);
+            valid = point_setup(m, srow, wc, lane, a.tlo, a.thi);
         }
         // what the rest of this iteration needs of the current item (the item variables are
         // re-used for the next one before the reduction)
@@ -1035,7 +1057,7 @@ __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc
                                                             const double *tables, const double *U,
                                                             double *theta, double *consts,
                                                             int *flags, long long B,
-                                                            int wstride)
+                                                            int wstride, double tlo, double thi)
 {
     const int lane = threadIdx.x & 31;
     // the model description is read many times per point: one cooperative copy to shared memory
@@ -1064,7 +1086,7 @@ __global__ void __launch_bounds__(256) point_prepare_kernel(const rvl_model_desc
         for (int i = lane; i < m.ndim; i += 32) srow[i] = row[i];
     }
     __syncwarp();
-    const bool valid = point_setup(m, srow, consts + (size_t)pt * wstride, lane);
+    const bool valid = point_setup(m, srow, consts + (size_t)pt * wstride, lane, tlo, thi);
     if (lane == 0) flags[pt] = valid ? 0 : 1;
 }
 
@@ -1213,6 +1235,7 @@ struct rvl_handle {
     // host copies of the staged inputs
     int N = 0, Npad = 0, n_inst = 0;
     std::vector<double> h_t, h_rv, h_err;
+    double tlo = 0.0, thi = 0.0;  // min / max of h_t
     std::vector<int32_t> h_inst;
     std::vector<double> h_linpar[RVL_MAX_LINPAR];
     bool have_data = false, have_model = false, have_priors = false, cols_dirty = true;
@@ -1499,7 +1522,7 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     PlanIn in{};
     in.Ctot = h->Npad / 32;
     in.ncol = h->ncol;
-    in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1) & ~1;
+    in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1 + 1) & ~1;  // (+1: the lean flag)
     in.wblock = in.wstride + ((m.ndim + 1) & ~1);
     // epochs per lane in flight: 4 (512 threads, 128 registers) when every warp has a long queue of
     // whole points -- the per-pass control instructions are then shared by four solves; 2 (896
@@ -1558,7 +1581,7 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
         const int wpb = 8;  // warps (= points) per block
         point_prepare_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, st>>>(
             h->d_model, h->d_priors, h->d_tables, dU, dTheta, h->d_consts, h->d_flags, B,
-            pl.wstride);
+            pl.wstride, h->tlo, h->thi);
         CU(h, cudaGetLastError());
         ++h->launches;
     }
@@ -1590,6 +1613,7 @@ int enqueue_loglike(rvl_t *h, const double *dU, double *dTheta, long long B, dou
     a.partial = h->d_partial; a.arrive = h->d_arrive; a.flags = h->d_flags;
     a.counters = h->d_counters; a.work = h->d_work;
     a.consts = prepare ? h->d_consts : nullptr;
+    a.tlo = h->tlo; a.thi = h->thi;
     a.B = B; a.ptS0 = pl.ptS0; a.cte = -0.5 * h->N * log(2 * M_PI); a.N = h->N; a.Npad = h->Npad;
     a.ncol = h->ncol; a.Sm = pl.Sm; a.cpm = pl.cpm; a.nitems = pl.nitems; a.nph = pl.nph;
     a.wstride = pl.wstride; a.wblock = pl.wblock;
@@ -2058,6 +2082,8 @@ int rvl_set_data(rvl_t *h, const double *t, const double *rv, const double *err,
     h->N = n; h->Npad = (n + 31) / 32 * 32; h->n_inst = n_inst;
     h->h_t.assign(t, t + n); h->h_rv.assign(rv, rv + n); h->h_err.assign(err, err + n);
     h->h_inst.assign(inst, inst + n);
+    h->tlo = *std::min_element(t, t + n);
+    h->thi = *std::max_element(t, t + n);
     for (auto &c : h->h_linpar) c.clear();
     h->have_data = true; h->cols_dirty = true;
     return RVL_OK;
