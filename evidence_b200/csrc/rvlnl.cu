@@ -202,6 +202,7 @@ constexpr int kHiSmall = 0x3FA00000;    // abs_hi(d) <  this  <=>  |d| <  2^-5
 #ifndef RVL_MEDIUM
 #define RVL_MEDIUM 1
 #endif
+constexpr int kHiMid = 0x3FC00000;      // abs_hi(d) <  this  <=>  |d| <  2^-3
 constexpr int kHiMedium = 0x3FE80000;   // abs_hi(d) <  this  <=>  |d| <  0.75
 
 template <int U>
@@ -264,6 +265,9 @@ __device__ __forceinline__ void solve_planet_ref(const rvl::KTab &kt, const doub
         } else if (VARIANT == 0 && wmax < kHiSmall) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_small(kt, d[u], s[u], c[u]);
+        } else if (VARIANT == 0 && !slow && wmax < kHiMid) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) rvl::advance_mid(kt, d[u], s[u], c[u]);
         } else if (VARIANT == 0 && !slow && wmax < kHiMedium) {
 #pragma unroll
             for (int u = 0; u < U; ++u) rvl::advance_medium(kt, d[u], s[u], c[u]);
@@ -384,8 +388,13 @@ __device__ __forceinline__ void solve_planet(const rvl::KTab &kt, const double (
                     for (int u = 0; u < U; ++u) rvl::advance_small(kt, d[u], s[u], c[u]);
                 }
             } else if (wmax < kHiMedium) {
+                if (wmax < kHiMid) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) rvl::advance_medium(kt, d[u], s[u], c[u]);
+                    for (int u = 0; u < U; ++u) rvl::advance_mid(kt, d[u], s[u], c[u]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) rvl::advance_medium(kt, d[u], s[u], c[u]);
+                }
             } else {
                 // |E| can only leave the fast range after >= 3 Newton steps (|step| <= 100 |f|)
                 if (trip > 2 && any_big<U>(E)) { fallback = true; break; }
@@ -586,7 +595,8 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
                       __double2hiint(tol) < rvl::kHiFinal && itmax >= 2;
     double chi = 0.0, prod = 1.0;
     int esum = 0, iters = 0, caps = 0;
-    bool ok = true;
+    uint32_t worst = 0;  // unsigned maximum of (sign + biased exponent of a variance) - 1
+    int nlive = 0;       // variances whose biased exponent went into esum
     for (int ch = c_lo; ch < c_hi; ch += U) {
         // U chunks of 32 epochs; a missing last chunk repeats the previous one, masked
         uint32_t off[U];
@@ -616,8 +626,8 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             const uint32_t ae = a_t + off[u];
             const int ii = lds_u8(a_inst + off[u] / 8u);
             const uint32_t ai = a_ic + (uint32_t)ii * 16u;
-            double rvm = lds_f64(ai);
-            if (K > 0) rvm = rvl::add(rvm, rvsum[u]);
+            const double rvm0 = rvl::add(lds_f64(ai), rvsum[u]);  // (rvsum is an exact 0 without planets)
+            double rvm = rvm0;
             if (has_drift) {
                 // lin*tt + quad*tt^2 + cub*tt^3 + quar*tt^4, left to right (:271); a
                 // coefficient that is absent from the model is an exact +0 term: skipped
@@ -641,14 +651,15 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             const double var = rvl::add(lds_f64(ae + 2u * colb), lds_f64(ai + 8));
             const double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
             double mant;
-            int ex;
-            const bool okv = rvl::split_pos(var, mant, ex);
+            uint32_t be;
+            rvl::split_raw(var, mant, be);
             if (live[u]) {
                 chi = rvl::add(chi, term);
                 prod = rvl::mul(prod, mant);
-                esum += ex;
-                ok = ok && okv;
+                esum += (int)be;  // biased: 1023 per term comes off at the end
+                worst = max(worst, be - 1u);
                 iters += it_l[u];
+                ++nlive;
             }
         }
         if (((ch - c_lo) & 255) >= 254) {  // keep the mantissa product in range
@@ -659,7 +670,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             esum += ee;
         }
     }
-    return ItemSums{chi, prod, esum, iters, caps, ok ? 1 : 0};
+    return ItemSums{chi, prod, esum - 1023 * nlive, iters, caps, worst < 0x7feu ? 1 : 0};
 }
 
 // Constants of a split point, published by a setup item: into the warp's block in shared memory.

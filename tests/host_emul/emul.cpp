@@ -31,7 +31,7 @@ inline double par_of(const rvl_param &p, const double *row) { return p.slot >= 0
 
 
 inline int abs_hi(double x) { return rvl::hi32(x) & 0x7fffffff; }
-constexpr int kHiTrigMax = 0x40F86A00, kHiTiny = 0x3F500000, kHiSmall = 0x3FA00000, kHiMedium = 0x3FE80000;
+constexpr int kHiTrigMax = 0x40F86A00, kHiTiny = 0x3F500000, kHiSmall = 0x3FA00000, kHiMid = 0x3FC00000, kHiMedium = 0x3FE80000;
 
 // one planet for U chunks of 32 epochs (U*32 solves) in lock-step: mirrors solve_planet<0, U>
 void solve_planet_warp(int U, const double *const *t, const double *pc, double tol, int itmax,
@@ -55,12 +55,13 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
     ++st.solves_warp;
     int trip = 0;
     for (;;) {
-        bool all_tiny = true, all_small = true, all_medium = true, any_big = false;
+        bool all_tiny = true, all_small = true, all_mid = true, all_medium = true, any_big = false;
         for (int u = 0; u < U; ++u)
             for (int l = 0; l < W; ++l) {
                 const int h = abs_hi(d[u][l]);
                 all_tiny = all_tiny && (h < kHiTiny);
                 all_small = all_small && (h < kHiSmall);
+                all_mid = all_mid && (h < kHiMid);
                 all_medium = all_medium && (h < kHiMedium);
                 any_big = any_big || !(abs_hi(E[u][l]) < kHiTrigMax);
             }
@@ -75,6 +76,7 @@ void solve_planet_warp(int U, const double *const *t, const double *pc, double t
         }
         if (all_tiny) { ++st.trips_tiny; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_tiny(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
         else if (all_small) { ++st.trips_small; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_small(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
+        else if (!slow && all_mid) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_mid(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
         else if (!slow && all_medium) { ++st.trips_medium; for (int u = 0; u < U; ++u) for (int l = 0; l < W; ++l) rvl::advance_medium(rvl::h_ktab, d[u][l], s[u][l], c[u][l]); }
         else {
             ++st.trips_full;
