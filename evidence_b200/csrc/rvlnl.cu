@@ -605,7 +605,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
         int it_l[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const bool have = (ch + u) < c_hi;
+            const bool have = U == 4 || (ch + u) < c_hi;  // (U = 4: whole trips, see rv_lnl_kernel)
             const int cu = have ? ch + u : ch;
             off[u] = (uint32_t)cu * 256u;
             live[u] = have && (e_base + cu * 32) < N;
@@ -709,9 +709,14 @@ __global__ void __launch_bounds__(THREADS, 1) rv_lnl_kernel(const KArgs a)
     static_assert(sizeof(HotCtx) <= 112, "HotCtx must fit in front of the model description");
     rvl_model_desc *sm = reinterpret_cast<rvl_model_desc *>(smem_raw + 128);
     const int sl = blockIdx.x % a.Sm;
-    const int Ctot = a.Npad / 32;
+    const int Ctot = (a.N + 31) / 32;
     const int c0 = sl * a.cpm;
-    const int nch = min(a.cpm, Ctot - c0);  // chunks resident in this block (>= 1 by construction)
+    // chunks resident in this block (>= 1 by construction); U = 4: in whole warp trips -- the
+    // columns in HBM are padded to whole groups of 4 chunks (the last epoch repeated), so a trip
+    // never meets a missing chunk, only masked epochs (the narrower builds keep the test: at 72
+    // registers the code without it spills more than it saves)
+    const int nch0 = min(a.cpm, Ctot - c0);
+    const int nch = U == 4 ? (nch0 + 3) / 4 * 4 : nch0;
     const int ne = nch * 32;
     double *scol = reinterpret_cast<double *>(smem_raw + 128 + kModelBytes);
     uint8_t *sinst = reinterpret_cast<uint8_t *>(scol + (size_t)a.ncol * ne);
@@ -1531,7 +1536,7 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
 {
     const rvl_model_desc &m = h->model;
     PlanIn in{};
-    in.Ctot = h->Npad / 32;
+    in.Ctot = (h->N + 31) / 32;  // (the columns themselves are padded further: see rvl_set_data)
     in.ncol = h->ncol;
     in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1 + 1) & ~1;  // (+1: the lean flag)
     in.wblock = in.wstride + ((m.ndim + 1) & ~1);
@@ -2090,7 +2095,9 @@ int rvl_set_data(rvl_t *h, const double *t, const double *rv, const double *err,
         return fail(h, RVL_EINVAL, "n_inst must be in [1, " + std::to_string(RVL_MAX_INST) + "]");
     for (int j = 0; j < n; ++j)
         if (inst[j] < 0 || inst[j] >= n_inst) return fail(h, RVL_EINVAL, "instrument id out of range");
-    h->N = n; h->Npad = (n + 31) / 32 * 32; h->n_inst = n_inst;
+    // padded (the last epoch repeated, masked in the kernel) to whole groups of 4 chunks of 32: a
+    // warp trip of U = 4 chunks then never meets a missing chunk
+    h->N = n; h->Npad = (n + 127) / 128 * 128; h->n_inst = n_inst;
     h->h_t.assign(t, t + n); h->h_rv.assign(rv, rv + n); h->h_err.assign(err, err + n);
     h->h_inst.assign(inst, inst + n);
     h->tlo = *std::min_element(t, t + n);

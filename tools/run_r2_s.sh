@@ -6,3 +6,5 @@ import json
 d=json.loads([l for l in open("gpurun_out/r2s_bench.log") if l.startswith("{")][-1])
 print("value %.5g"%d["value"], "ms %.3f"%d["ms_per_step"], "e2e %.5g"%d["e2e"]["value"], "frac", d["roofline"]["frac"], d["parity"]["pass"], d["parity"]["max_abs"])
 PY
+python tools/prof_sweep.py 2 4096 0 | tail -1
+python tools/prof_sweep.py 3 10000 0 | tail -1
