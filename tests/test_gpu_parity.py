@@ -188,6 +188,63 @@ def test_larger_batch_vs_c_oracle(models):
     assert abs(c["n_newton_iters"] - iters) <= 1e-6 * iters + 5, (c["n_newton_iters"], iters)
 
 
+@pytest.mark.parametrize("case_name", ["short_periods", "loose_tolerance"])
+def test_general_loop_vs_c_oracle(models, case_name):
+    """The solves of a point leave the lean Newton loop when point_setup finds a mean anomaly
+    outside the fast sin/cos range (|n| max|t - epoch| + |M0| >= 1e5: periods of minutes), and
+    every point does for a tolerance above 2e-4; both then run the general loop (libdevice
+    sin/cos where needed).  Same results and the same Newton iteration totals as the plain-C
+    restatement; a batch mixes both kinds of rows."""
+    from evidence_b200 import synth
+    from oracle import rv_oracle
+    meta, z, _ = models("cfg3")
+    case = synth.make_case(3)
+    theta = case.draw_theta(256, seed=31)
+    kw = {}
+    if case_name == "short_periods":
+        rng = np.random.default_rng(4)
+        names = sorted(meta["parnames"])
+        for p in (1, 3):  # |M| up to 2 pi 2500 / 0.02 = 8e5 on every second row
+            j = names.index(f"planet{p}_period")
+            theta[::2, j] = rng.uniform(0.02, 0.1, size=theta[::2].shape[0])
+    else:
+        kw = dict(tol=1e-3)
+    m = device_model(meta, z, **kw)
+    om = oracle_model(meta, z)
+    want, iters, caps = rv_oracle.c_loglike_batch(m.desc_bytes(), om.time, om.vrad, om.svrad,
+                                                  om.inst_id, len(meta["insts"]), theta)
+    got = m.log_likelihood_batch(theta)
+    c = m.counters()
+    m.close()
+    # (short periods: sin/cos of arguments up to 8e5 -- libdevice against glibc, both below an ulp)
+    ok, worst = lnl_close(got, want)
+    assert ok, (case_name, worst)
+    assert abs(c["n_newton_iters"] - iters) <= 1e-6 * iters + 5, (case_name, c["n_newton_iters"], iters)
+    assert c["n_cap_hits"] == 0 and caps == 0
+
+
+def test_cap_exit_of_the_lean_loop_matches_the_general_loop(models):
+    """At the iteration cap the lean loop finishes on the spot (its own copy of the velocity
+    formula); the conservative build runs the general loop.  Same lnL, the same cap hits and the
+    same iteration totals, for caps that cut the solves short at every stage."""
+    from evidence_b200 import synth
+    meta, z, _ = models("cfg2")
+    case = synth.make_case(2)
+    theta = case.draw_theta(300, seed=17)
+    for itmax in (2, 3, 5):
+        res = []
+        for variant in (0, 1):
+            m = device_model(meta, z, itmax=itmax)
+            m.set_option("variant", variant)
+            res.append((m.log_likelihood_batch(theta), m.counters()))
+            m.close()
+        (a, ca), (b, cb) = res
+        assert ca["n_cap_hits"] > 0 and ca["n_cap_hits"] == cb["n_cap_hits"], (itmax, ca, cb)
+        assert ca["n_newton_iters"] == cb["n_newton_iters"], (itmax, ca, cb)
+        ok, worst = lnl_close(a, b)
+        assert ok, (itmax, worst)
+
+
 def test_full_size_properties():
     """BASELINE sizes (config 3, 1e5 points): properties that need no oracle."""
     from evidence_b200 import synth
