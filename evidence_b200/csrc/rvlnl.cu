@@ -218,7 +218,7 @@ __device__ __forceinline__ bool any_big(const double (&E)[U])
 // Lanes freeze individually (trueanomaly.c:21: per-element stop): a frozen lane's step is exactly
 // 0, so its E never moves again and `|d| > tol` keeps it inactive without a separate flag.
 // iters[u] counts the Newton steps BEYOND the first (every solve takes at least one: the caller
-// starts the count at one per planet).
+// adds one per planet and live epoch).
 //
 // solve_planet_ref: the plain statement of the loop -- any tolerance, any |M| (libdevice sin/cos
 // when an argument is >= 1e5 or not finite), VARIANT 1 = IEEE division + full sin/cos every step.
@@ -617,7 +617,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             live[u] = have && (e_base + cu * 32) < N;
             t[u] = lds_f64(a_t + off[u]);
             rvsum[u] = 0.0;
-            it_l[u] = K;  // every solve takes at least one Newton step; solve_planet adds the rest
+            it_l[u] = 0;  // steps after the first; the first of each solve is added with nlive below
         }
         int cap_l = 0;
         for (int p = 0; p < K; ++p) {
@@ -665,7 +665,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
                 esum += (int)be;  // biased: 1023 per term comes off at the end
                 worst = max(worst, be - 1u);
                 iters += it_l[u];
-                ++nlive;
+                ++nlive;  // (also: K first Newton steps, one per planet)
             }
         }
         if (((ch - c_lo) & 255) >= 254) {  // keep the mantissa product in range
@@ -676,7 +676,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             esum += ee;
         }
     }
-    return ItemSums{chi, prod, esum - 1023 * nlive, iters, caps, worst < 0x7feu ? 1 : 0};
+    return ItemSums{chi, prod, esum - 1023 * nlive, iters + K * nlive, caps, worst < 0x7feu ? 1 : 0};
 }
 
 // Constants of a split point, published by a setup item: into the warp's block in shared memory.
