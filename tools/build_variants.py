@@ -7,7 +7,10 @@ from evidence_b200 import build
 VARIANTS = {
     "nopin": ["RVL_PIN_KTAB=0"],   # constants re-loaded by the compiler where it likes
     "no_fma_f": ["RVL_FMA_F=0"],   # two-rounding E - e sin E
-    "norot": ["RVL_ROT_FUSED=0"],  # rotation as old value + small correction (6 instructions)
+    "norot": ["RVL_ROT_FUSED=0", "RVL_ROT_CD=0", "RVL_ROT_SHEAR=0"],  # rotation as old value + small correction (6 instructions)
+    "noshear": ["RVL_ROT_SHEAR=0"],  # short series: four-FMA rotation instead of three in-place shears
+    "nocd": ["RVL_ROT_CD=0"],        # long series: s' = fma(c, sd, fma(-s, v, s)) (one register move per pass)
+    "nopinwc": ["RVL_PIN_WC=0"],     # the warp's constant-block address re-derived per planet
 }
 if __name__ == "__main__":
     d = os.path.join(os.path.dirname(build.OUT), "variants")
