@@ -599,6 +599,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
     // the lean Newton loop: the point's flag (point_setup) and the launch-wide conditions
     const bool lean = lds_u32(a_dc + 32u + (uint32_t)nlin * 8u + 4u) != 0u &&
                       __double2hiint(tol) < rvl::kHiFinal && itmax >= 2;
+    const bool extras = has_drift || nlin > 0;
     double chi = 0.0, prod = 1.0;
     int esum = 0, iters = 0, caps = 0;
     uint32_t worst = 0;  // unsigned maximum of (sign + biased exponent of a variance) - 1
@@ -634,6 +635,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             const uint32_t ai = a_ic + (uint32_t)ii * 16u;
             const double rvm0 = rvl::add(lds_f64(ai), rvsum[u]);  // (rvsum is an exact 0 without planets)
             double rvm = rvm0;
+            if (extras) {  // (one uniform test for the plain model: offsets + Keplerians only)
             if (has_drift) {
                 // lin*tt + quad*tt^2 + cub*tt^3 + quar*tt^4, left to right (:271); a
                 // coefficient that is absent from the model is an exact +0 term: skipped
@@ -653,6 +655,7 @@ __device__ RVL_ITEM_INLINE ItemSums item_epochs(const rvl::KTab &kt, const HotCt
             for (int l = 0; l < nlin; ++l)
                 rvm = rvl::add(rvm, rvl::mul(lds_f64(a_dc + 32u + (uint32_t)l * 8u),
                                              lds_f64(ae + lin0 + (uint32_t)l * colb)));
+            }
             const double res = rvl::sub(lds_f64(ae + colb), rvm);
             const double var = rvl::add(lds_f64(ae + 2u * colb), lds_f64(ai + 8));
             const double term = rvl::mul(rvl::mul(res, res), rvl::rcp(rvl::add(var, var)));
