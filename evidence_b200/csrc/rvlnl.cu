@@ -1550,11 +1550,17 @@ int make_plan(rvl_t *h, long long B, Plan &pl)
     in.wstride = (m.n_planets * kPlanetStride + 2 * m.n_inst + 4 + m.n_linpar + 1 + 1) & ~1;  // (+1: the lean flag)
     in.wblock = in.wstride + ((m.ndim + 1) & ~1);
     // epochs per lane in flight: 4 (512 threads, 128 registers) when every warp has a long queue of
-    // whole points -- the per-pass control instructions are then shared by four solves; 2 (896
-    // threads, 72 registers) for sampler-sized batches, where the drain matters more (measured, B200:
-    // config 3 at 131072 theta 24.76 vs 25.08 ms; config 2 at 4096 theta 0.137 vs 0.153 ms)
+    // whole points AND a point is long enough to amortise its setup over the 16 warps per SM left --
+    // the per-pass control instructions are then shared by four solves; 2 (896 threads, 72 registers)
+    // for sampler-sized batches and for short or planet-poor points, where the drain and the
+    // per-point work matter more.  Measured, B200, final build, U = 2 against U = 4: config 3
+    // (N 5000, K 4) at 524288 theta U = 4 wins; the same at N 2500 / 1250: a tie; config 2 (K 2,
+    // drift) at 1048576 theta 19.8 vs 23.8 ms, at N 4000 18.9 vs 19.7; config 5 (N 10000, K 3) at 131072
+    // theta 33.5 vs 33.9 ms; config 1 (N 200, K 1) 2.9 vs 3.8 ms; config 2 at 4096 theta 0.110 vs 0.125.
     int ilp = h->opt_ilp;
-    if (ilp == 0) ilp = (B >= (long long)h->sm_count * 16 * 16) ? 4 : 2;
+    if (ilp == 0)
+        ilp = (B >= (long long)h->sm_count * 16 * 16 && m.n_planets >= 4 &&
+               (long long)h->N * m.n_planets >= 16384) ? 4 : 2;
     in.U = h->opt_variant == 0 ? ilp : 1;
     const int w_default = in.U == 1 ? 32 : in.U == 2 ? 28 : in.U == 3 ? 20 : 16;
     const int w_max = in.U <= 2 ? 32 : in.U == 3 ? 20 : 16;

@@ -5,7 +5,8 @@ from evidence_b200 import synth
 from evidence_b200.rvmodel import RVModel
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-case = synth.make_case(cfg)
+nep = [int(a.split('=')[1]) for a in sys.argv[4:] if a.startswith('epochs=')]
+case = synth.make_case(cfg, n_epochs=nep[0]) if nep else synth.make_case(cfg)
 m = RVModel(case.fixedpardict, case.datadict(), case.parnames)
 m.set_option("timing", 1)
 ilp = int(sys.argv[3]) if len(sys.argv) > 3 else 2
@@ -15,7 +16,7 @@ if len(sys.argv) > 4 and "=" not in sys.argv[4]:
 if len(sys.argv) > 5 and "=" not in sys.argv[5]:
     m.set_option("slices", int(sys.argv[5]))
 for kv in sys.argv[4:]:
-    if "=" in kv:
+    if "=" in kv and not kv.startswith("epochs="):
         k, v = kv.split("=")
         m.set_option(k, int(v))
 th = torch.from_numpy(case.draw_theta(B, seed=77)).cuda()
