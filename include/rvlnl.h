@@ -184,7 +184,8 @@ int rvl_set_priors(rvl_t *h, const rvl_prior_desc *priors, int32_t ndim, const d
  *               axis needs several resident ranges; 2: in place even then (through the
  *               once-per-point pass); 0: stage everything with cudaMemcpyAsync
  *   "variant"   0 optimised kernel (default), 1 conservative cross-check (IEEE division, full sin/cos)
- *   "ilp"       epochs per lane in flight, 1..4; 0 (default): 4 for large batches, 2 otherwise
+ *   "ilp"       epochs per lane in flight, 1..4; 0 (default): 4 for large batches of long points with
+ *               four or more planets (N K >= 16384), 2 otherwise
  *   "sched"     1 (default): graded work list -- whole points first, then the points at the end of the
  *               batch cut into 2, 4, .. "max_split" (8) sub-slices with about "phase_items" (200)
  *               percent of one item per warp in each phase, so that all warps run dry together;
@@ -288,7 +289,7 @@ int rvl_fp64_peak(rvl_t *h, double *tflops);
  * reads the rows of the last launch (tools/warp_trace.py draws the drain curve from them). */
 int rvl_read_trace(rvl_t *h, uint64_t *out, int32_t cap_rows, int32_t *rows);
 /* The launch plan as data (no device needed; tests/test_plan.py checks that the work items cover
- * every (point, epoch chunk) exactly once).  in[13] = { Npad/32, ncol, wstride, ilp, warps,
+ * every (point, epoch chunk) exactly once).  in[13] = { ceil(N/32), ncol, wstride, ilp, warps,
  * sm_count, smem_optin, sched, slices, items_per_warp, min_chunks, phase_items, max_split };
  * out[0..8) = { Sm, cpm, grid, n_phases, items per queue, first split point, split points,
  * partial-sum doubles }, then per phase { idx0, S, cps, pt0, part0 }. */
