@@ -1,3 +1,5 @@
+# round 2, GPU call T (1 GPU): experiment -- U = 6 (384 threads) and U = 8 (256 threads) builds of the likelihood kernel
+# against U = 4; those instantiations were NOT kept (100.4 and 183 ms against 92.5), so "ilp" 6 / 8 is refused today
 set -x
 for ilp in 4 6 8; do
 python tools/prof_sweep.py 3 524288 $ilp | tail -1
