@@ -11,15 +11,18 @@
 //
 // Layout.  Epoch data lives in HBM as columns [ncol][Npad] of doubles (t, vrad, svrad^2, then
 // (t-tref)/365.25 when the model has a drift, then the linear-parameter columns) followed by
-// Npad instrument ids (uint8).  The epoch axis is cut into S slices of whole 32-epoch chunks;
-// block b serves slice b % S and brings that slice of every column into shared memory ONCE with
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier), then stays resident: its warps pull parameter
-// vectors from a per-slice work counter.  warp <-> one parameter vector, lanes <-> 32 epochs:
-// all lanes of a warp share the eccentricity, so Newton iteration counts are nearly uniform and
-// the loop exit / sin-cos path choice come from one warp redux per trip.  chi^2 and log-det sums are
-// reduced with warp shuffles; with S > 1 a one-warp-per-point prepare pass computes the per-point
-// constants once (optionally fused with the prior transform), every slice writes its partial sums
-// and a small second kernel adds them in slice order (deterministic).
+// Npad instrument ids (uint8); Npad = N rounded up to whole groups of four 32-epoch chunks (the last
+// epoch repeated, masked).  The epoch axis is cut into Sm resident ranges of whole chunks -- the
+// fewest that fit shared memory; block b serves range b % Sm and brings that range of every column
+// into shared memory ONCE with 1-D TMA bulk copies (cp.async.bulk + mbarrier), then stays resident:
+// its warps pull work items -- (point, sub-slice of the range) in phases from coarse to fine, see
+// Phase below -- from a per-range work counter.  warp <-> one item, lanes <-> 32 epochs (x U = 2 or 4
+// chunks in flight): all lanes of a warp share the eccentricity, so Newton iteration counts are
+// nearly uniform and the loop exit / sin-cos path choice come from one warp redux per trip.  chi^2
+// and log-det sums are reduced with warp shuffles.  A point that is cut into several items has its
+// per-point constants derived once by a setup item at the head of the list (or by the prepare pass
+// of the fused prior transform); every item writes its partial sums and the LAST item of the point
+// to arrive adds them in slice order (deterministic) -- one launch per likelihood call.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
